@@ -1,0 +1,120 @@
+/*
+ * fft_b200.h — C ABI of libfft_b200, the B200 (sm_100a) FFT engine that sits behind
+ * Regent-FFT's GPU branch.
+ *
+ * Pure C (no C++, no default arguments) so that Terra's `terralib.includec` can parse
+ * it exactly as it parses cufftXt.h today (reference src/fft.rg:15-20).  Constants are
+ * `enum`s, not `#define`s: includec drops macros (cf. src/fft.rg:22-25, where the
+ * FFTW macros are re-declared by hand).
+ *
+ * Every entry point replaces one cuFFT call site of the reference:
+ *
+ *   fftb200_plan_many   <- cufftPlanMany   src/fft.rg:233,236,239,242 (make_plan_gpu)
+ *                                          src/fft.rg:389,392,395,398 (make_plan_gpu_batch)
+ *   fftb200_exec_c2c    <- cufftExecC2C    src/fft.rg:574
+ *   fftb200_exec_z2z    <- cufftExecZ2Z    src/fft.rg:580
+ *   fftb200_exec_d2z    <- cufftExecD2Z    src/fft.rg:577
+ *   fftb200_exec_r2c    <- cufftExecR2C    src/fft.rg:571 (commented out upstream; README.md:16 promises it)
+ *   fftb200_destroy     <- cufftDestroy    src/fft.rg:638
+ *   fftb200_set_stream  <- (cufftSetStream; the reference relies on the default stream, src/fft.rg:563-581)
+ *
+ * Semantics held:
+ *   - forward transforms are unnormalised, sign -1 (src/fft.rg:22,574,580); backward (+1) is also
+ *     provided for C2C/Z2Z;
+ *   - out-of-place, input preserved (privilege reads(input), src/fft.rg:545); in == out is accepted
+ *     for C2C/Z2Z;
+ *   - inembed == NULL  => cuFFT "basic" layout: packed row-major, batches back to back, R2C/D2Z
+ *     output rows of n[rank-1]/2+1 complex (stride/dist arguments ignored, as cuFFT does);
+ *   - inembed != NULL  => advanced layout, element (b, j0..jr-1) at
+ *     b*dist + (((j0*embed[1] + j1)*embed[2] + ...) + j_last)*stride, input embed counted in
+ *     input elements, output embed in output elements (fftw-3.3.8/api/plan-many-dft.c:43-46,
+ *     api/plan-many-dft-r2c.c:44-49);
+ *   - n[i] is taken as given (the reference passes Regent extents as row-major dims,
+ *     src/fft.rg:220-223; the library does not reorder);
+ *   - asynchronous with respect to the host, ordered on the plan's stream (default: stream 0);
+ *   - return value 0 == success; 1 and 4 keep cuFFT's meaning so fft.rg's checks
+ *     (src/fft.rg:246-250, 584-591) keep working; nothing throws or aborts across the ABI;
+ *   - handles are plain 64-bit integers (0 = null) that survive being memcpy'd inside the plan
+ *     region (src/fft.rg:48-65); destroy(0) is a no-op and destroy needs no current device
+ *     (src/fft.rg:523-531, 624-645).
+ *   - thread-safe across plans (Legion runs one task per GPU processor concurrently).
+ *
+ * There is no CPU fallback: every exec runs hand-written sm_100a kernels or fails.
+ */
+#ifndef FFT_B200_H
+#define FFT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__) || defined(__clang__)
+#define FFTB200_API __attribute__((visibility("default")))
+#else
+#define FFTB200_API
+#endif
+
+typedef unsigned long long fftb200_handle; /* POD; 0 == null; storable by value in iface.plan */
+
+/* same numeric codes as cufftType (cufft.h) so the type selection at src/fft.rg:231-243 maps 1:1 */
+typedef enum fftb200_type_e {
+    FFTB200_R2C = 0x2a, /* float   -> complex32 */
+    FFTB200_C2C = 0x29, /* complex32 -> complex32 */
+    FFTB200_D2Z = 0x6a, /* double  -> complex64 */
+    FFTB200_Z2Z = 0x69  /* complex64 -> complex64 */
+} fftb200_type;
+
+typedef enum fftb200_result_e {
+    FFTB200_SUCCESS = 0,
+    FFTB200_INVALID_PLAN = 1,
+    FFTB200_ALLOC_FAILED = 2,
+    FFTB200_INVALID_TYPE = 3,
+    FFTB200_INVALID_VALUE = 4,
+    FFTB200_INTERNAL_ERROR = 5,
+    FFTB200_EXEC_FAILED = 6,
+    FFTB200_SETUP_FAILED = 7,
+    FFTB200_INVALID_SIZE = 8,
+    FFTB200_UNSUPPORTED = 16
+} fftb200_result;
+
+enum { FFTB200_FORWARD = -1, FFTB200_INVERSE = 1 };
+
+/* Plan creation.  Call with the target GPU current (a Legion TOC processor's host thread). */
+FFTB200_API int fftb200_plan_many(fftb200_handle *plan, int rank, const int *n,
+                      const int *inembed, int istride, int idist,
+                      const int *onembed, int ostride, int odist,
+                      fftb200_type type, int batch);
+
+/* Bind later execs of this plan to a CUDA stream (cudaStream_t passed as void*). */
+FFTB200_API int fftb200_set_stream(fftb200_handle plan, void *cuda_stream);
+
+FFTB200_API int fftb200_exec_c2c(fftb200_handle plan, const void *in, void *out, int direction);
+FFTB200_API int fftb200_exec_z2z(fftb200_handle plan, const void *in, void *out, int direction);
+FFTB200_API int fftb200_exec_r2c(fftb200_handle plan, const void *in, void *out);
+FFTB200_API int fftb200_exec_d2z(fftb200_handle plan, const void *in, void *out);
+
+/* Free the plan's device tables and work buffers.  Any thread; no current device needed. */
+FFTB200_API int fftb200_destroy(fftb200_handle plan);
+
+/* ---- introspection (benchmarks, tests; no reference counterpart) ------------------------- */
+
+/* Bytes of device work area the plan owns (cf. cufftGetSize). */
+FFTB200_API int fftb200_get_work_size(fftb200_handle plan, unsigned long long *bytes);
+/* Number of kernel launches one exec issues, and a human-readable pass list
+ * ("name L=512 tiles=32768 ...", one line per launch) copied into buf (NUL-terminated). */
+FFTB200_API int fftb200_get_launch_count(fftb200_handle plan, int *launches);
+FFTB200_API int fftb200_describe(fftb200_handle plan, char *buf, int buflen);
+/* Algorithmic HBM bytes of launch `i` (elements read * sizeof(in) + elements written * sizeof(out)). */
+FFTB200_API int fftb200_get_launch_bytes(fftb200_handle plan, int i, unsigned long long *bytes);
+/* Record per-launch CUDA events on the next execs (on=1) and read back launch i's last duration. */
+FFTB200_API int fftb200_set_profiling(fftb200_handle plan, int on);
+FFTB200_API int fftb200_get_launch_ms(fftb200_handle plan, int i, float *ms);
+
+FFTB200_API const char *fftb200_strerror(int code);
+/* library version: major*10000 + minor*100 + patch */
+FFTB200_API int fftb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFT_B200_H */

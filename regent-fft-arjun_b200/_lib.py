@@ -1,0 +1,145 @@
+"""ctypes binding of libfft_b200.so (include/fft_b200.h).
+
+This is the Python twin of what `terralib.includec("fft_b200.h")` +
+`terralib.linklibrary("libfft_b200.so")` give Regent (reference src/fft.rg:15-20 does the same
+for cufftXt.h / libcufft.so).  There is NO fallback: if the shared library is missing or does
+not export a declared symbol, import fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfft_b200.so")
+
+# enums of include/fft_b200.h
+R2C, C2C, D2Z, Z2Z = 0x2A, 0x29, 0x6A, 0x69
+SUCCESS, INVALID_PLAN, ALLOC_FAILED, INVALID_TYPE, INVALID_VALUE = 0, 1, 2, 3, 4
+INTERNAL_ERROR, EXEC_FAILED, SETUP_FAILED, INVALID_SIZE, UNSUPPORTED = 5, 6, 7, 8, 16
+FORWARD, INVERSE = -1, 1
+
+_handle = ctypes.c_ulonglong
+_ip = ctypes.POINTER(ctypes.c_int)
+_vp = ctypes.c_void_p
+
+# every symbol the header declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "fftb200_plan_many": (ctypes.c_int, [ctypes.POINTER(_handle), ctypes.c_int, _ip, _ip, ctypes.c_int, ctypes.c_int,
+                                         _ip, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "fftb200_set_stream": (ctypes.c_int, [_handle, _vp]),
+    "fftb200_exec_c2c": (ctypes.c_int, [_handle, _vp, _vp, ctypes.c_int]),
+    "fftb200_exec_z2z": (ctypes.c_int, [_handle, _vp, _vp, ctypes.c_int]),
+    "fftb200_exec_r2c": (ctypes.c_int, [_handle, _vp, _vp]),
+    "fftb200_exec_d2z": (ctypes.c_int, [_handle, _vp, _vp]),
+    "fftb200_destroy": (ctypes.c_int, [_handle]),
+    "fftb200_get_work_size": (ctypes.c_int, [_handle, ctypes.POINTER(ctypes.c_ulonglong)]),
+    "fftb200_get_launch_count": (ctypes.c_int, [_handle, _ip]),
+    "fftb200_describe": (ctypes.c_int, [_handle, ctypes.c_char_p, ctypes.c_int]),
+    "fftb200_get_launch_bytes": (ctypes.c_int, [_handle, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]),
+    "fftb200_set_profiling": (ctypes.c_int, [_handle, ctypes.c_int]),
+    "fftb200_get_launch_ms": (ctypes.c_int, [_handle, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
+    "fftb200_strerror": (ctypes.c_char_p, [ctypes.c_int]),
+    "fftb200_version": (ctypes.c_int, []),
+}
+
+
+class FFTB200Error(RuntimeError):
+    def __init__(self, code: int, where: str):
+        self.code = code
+        msg = lib().fftb200_strerror(code).decode() if _lib is not None else "?"
+        super().__init__(f"{where} failed: {msg} (code {code})")
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load libfft_b200.so once.  Raises if it is absent: the product has no other path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `make -C regent-fft-arjun_b200` "
+                "(or __graft_entry__.build()).  There is no CPU or library fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code: int, where: str) -> None:
+    if code != SUCCESS:
+        raise FFTB200Error(code, where)
+
+
+def _ints(v):
+    return None if v is None else (ctypes.c_int * len(v))(*[int(x) for x in v])
+
+
+def plan_many(rank, n, inembed, istride, idist, onembed, ostride, odist, ftype, batch) -> int:
+    h = _handle(0)
+    rc = lib().fftb200_plan_many(ctypes.byref(h), rank, _ints(n), _ints(inembed), istride, idist,
+                                 _ints(onembed), ostride, odist, ftype, batch)
+    check(rc, "fftb200_plan_many")
+    return int(h.value)
+
+
+def set_stream(h: int, stream_ptr: int) -> None:
+    check(lib().fftb200_set_stream(h, stream_ptr), "fftb200_set_stream")
+
+
+def execute(h: int, ftype: int, in_ptr: int, out_ptr: int, direction: int = FORWARD) -> None:
+    L = lib()
+    if ftype == Z2Z:
+        rc = L.fftb200_exec_z2z(h, in_ptr, out_ptr, direction)
+    elif ftype == C2C:
+        rc = L.fftb200_exec_c2c(h, in_ptr, out_ptr, direction)
+    elif ftype == D2Z:
+        rc = L.fftb200_exec_d2z(h, in_ptr, out_ptr)
+    elif ftype == R2C:
+        rc = L.fftb200_exec_r2c(h, in_ptr, out_ptr)
+    else:
+        raise ValueError("bad transform type")
+    check(rc, "fftb200_exec")
+
+
+def destroy(h: int) -> None:
+    check(lib().fftb200_destroy(h), "fftb200_destroy")
+
+
+def describe(h: int) -> str:
+    buf = ctypes.create_string_buffer(8192)
+    check(lib().fftb200_describe(h, buf, len(buf)), "fftb200_describe")
+    return buf.value.decode()
+
+
+def launch_count(h: int) -> int:
+    n = ctypes.c_int(0)
+    check(lib().fftb200_get_launch_count(h, ctypes.byref(n)), "fftb200_get_launch_count")
+    return n.value
+
+
+def launch_bytes(h: int, i: int) -> int:
+    b = ctypes.c_ulonglong(0)
+    check(lib().fftb200_get_launch_bytes(h, i, ctypes.byref(b)), "fftb200_get_launch_bytes")
+    return int(b.value)
+
+
+def work_size(h: int) -> int:
+    b = ctypes.c_ulonglong(0)
+    check(lib().fftb200_get_work_size(h, ctypes.byref(b)), "fftb200_get_work_size")
+    return int(b.value)
+
+
+def set_profiling(h: int, on: bool) -> None:
+    check(lib().fftb200_set_profiling(h, 1 if on else 0), "fftb200_set_profiling")
+
+
+def launch_ms(h: int, i: int) -> float:
+    ms = ctypes.c_float(0)
+    check(lib().fftb200_get_launch_ms(h, i, ctypes.byref(ms)), "fftb200_get_launch_ms")
+    return float(ms.value)

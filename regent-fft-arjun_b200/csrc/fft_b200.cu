@@ -1,0 +1,866 @@
+// fft_b200.cu — plan builder, executor and the C ABI of libfft_b200 (include/fft_b200.h).
+//
+// This is the layer that replaces cuFFT behind Regent-FFT's GPU branch
+// (reference src/fft.rg:233-242, 389-398, 571-580, 638).  A plan is a short list of kernel
+// launches ("passes"); every pass is one HBM round trip over one axis:
+//
+//   3-D C2C  [n0][n1][n2] : ROW pass over n2 (in -> out), COL pass over n1, COL pass over n0 (in place)
+//   R2C                   : the first pass is the fused half-length FFT + even/odd post-pass,
+//                           later passes run over n_last/2+1 columns
+//   1-D N > one tile      : four-step, N = N1*N2(*N3): COL+twiddle pass(es), then a transposing
+//                           ROW->COL pass, through the plan's work buffer
+//   anything else         : generic global-memory path (generic_kernels.cuh)
+//
+// No CPU fallback exists: if a kernel cannot be launched the call returns an error code.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fft_b200.h"
+#include "generic_kernels.cuh"
+#include "tile_registry.h"
+
+namespace fftb200 {
+
+// ------------------------------------------------------------------------------------------
+// kernel registry
+// ------------------------------------------------------------------------------------------
+typedef const TileKernelInfo *(*table_fn)(int *);
+static table_fn k_tables[2][V_COUNT] = {
+    {tile_table_f32_rr, tile_table_f32_cc, tile_table_f32_cctw, tile_table_f32_rc, tile_table_f32_r2c},
+    {tile_table_f64_rr, tile_table_f64_cc, tile_table_f64_cctw, tile_table_f64_rc, tile_table_f64_r2c}};
+
+const TileKernelInfo *find_tile_kernel(int prec, int variant, int L) {
+    int n = 0;
+    const TileKernelInfo *t = k_tables[prec][variant](&n);
+    for (int i = 0; i < n; ++i)
+        if (t[i].L == L) return &t[i];
+    return nullptr;
+}
+
+int max_tile_length(int prec) {
+    int n = 0, m = 0;
+    const TileKernelInfo *t = k_tables[prec][V_RR](&n);
+    for (int i = 0; i < n; ++i) m = t[i].L > m ? t[i].L : m;
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// twiddles: w_n^m = exp(-2*pi*i*m/n), octant-reduced like fftw-3.3.8/kernel/trig.c:57-80, but
+// evaluated in long double before rounding (the accuracy contract of SURVEY.md §8 a10)
+// ------------------------------------------------------------------------------------------
+static void twiddle(long long m, long long n, double *re, double *im) {
+    static const long double K2PI = 6.2831853071795864769252867665590057683943388L;
+    unsigned octant = 0;
+    long long quarter_n = n;
+    n *= 4;
+    m *= 4;
+    if (m < 0) m += n;
+    if (m > n - m) { m = n - m; octant |= 4; }
+    if (m - quarter_n > 0) { m = m - quarter_n; octant |= 2; }
+    if (m > quarter_n - m) { m = quarter_n - m; octant |= 1; }
+    const long double theta = (K2PI * (long double)m) / (long double)n;
+    long double c = cosl(theta), s = sinl(theta), t;
+    if (octant & 1) { t = c; c = s; s = t; }
+    if (octant & 2) { t = c; c = -s; s = t; }
+    if (octant & 4) { s = -s; }
+    *re = (double)c;
+    *im = (double)(-s);  // forward sign
+}
+
+enum BufSel { BUF_IN = 0, BUF_OUT = 1, BUF_WORK0 = 2, BUF_WORK1 = 3 };
+
+struct Launch {
+    enum Kind { TILE, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER } kind = TILE;
+    // TILE
+    const TileKernelInfo *ki = nullptr;
+    TileParams tp{};
+    // generic
+    GenLayout lay{};
+    long long total = 0, outer = 0, inner = 0;
+    int L = 0, p = 0, Ns = 0, Lc = 0;
+    const double2 *gtw = nullptr;
+    bool real_in = false;
+    // common
+    int src = BUF_IN, dst = BUF_OUT;
+    unsigned grid = 0;
+    unsigned long long algo_bytes = 0;
+    std::string desc;
+};
+
+struct Plan {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    fftb200_type type = FFTB200_Z2Z;
+    int prec = 1;       // 0 fp32, 1 fp64
+    bool real = false;  // R2C / D2Z
+    bool generic = false;
+    bool inplace_ok = false;  // in == out allowed
+    std::vector<Launch> launches;
+    std::vector<void *> dev_allocs;
+    void *work[2] = {nullptr, nullptr};
+    size_t work_bytes = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;
+    std::vector<float> last_ms;
+    // saved creation arguments (lazy generic fallback for misaligned pointers)
+    int rank = 0, batch = 1;
+    long long n[3] = {1, 1, 1};
+    long long in_stride[4] = {0, 0, 0, 0}, out_stride[4] = {0, 0, 0, 0};  // [batch, d0, d1, d2] elements
+    std::unique_ptr<Plan> fallback;
+    std::mutex mu;
+    size_t elt_in() const { return real ? (prec ? 8 : 4) : (prec ? 16 : 8); }
+    size_t elt_out() const { return prec ? 16 : 8; }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+static void free_plan_resources(Plan *p) {
+    DeviceGuard g(p->device);
+    for (void *d : p->dev_allocs) cudaFree(d);
+    p->dev_allocs.clear();
+    for (cudaEvent_t e : p->events) cudaEventDestroy(e);
+    p->events.clear();
+    if (p->fallback) free_plan_resources(p->fallback.get());
+}
+
+// ------------------------------------------------------------------------------------------
+// handle table: handle = (generation << 32) | (slot + 1); never a raw pointer, so a stale or
+// zero-filled plan region (src/fft.rg:523-531) cannot crash the library
+// ------------------------------------------------------------------------------------------
+static std::mutex g_mu;
+static std::vector<std::pair<unsigned, Plan *>> g_slots;  // (generation, plan)
+
+static fftb200_handle register_plan(Plan *p) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (size_t i = 0; i < g_slots.size(); ++i)
+        if (!g_slots[i].second) {
+            g_slots[i].first++;
+            g_slots[i].second = p;
+            return ((fftb200_handle)g_slots[i].first << 32) | (fftb200_handle)(i + 1);
+        }
+    g_slots.push_back({1u, p});
+    return ((fftb200_handle)1 << 32) | (fftb200_handle)g_slots.size();
+}
+
+static Plan *lookup_plan(fftb200_handle h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const size_t slot = (size_t)(h & 0xffffffffull);
+    const unsigned gen = (unsigned)(h >> 32);
+    if (slot == 0 || slot > g_slots.size()) return nullptr;
+    if (g_slots[slot - 1].first != gen) return nullptr;
+    return g_slots[slot - 1].second;
+}
+
+static Plan *unregister_plan(fftb200_handle h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const size_t slot = (size_t)(h & 0xffffffffull);
+    const unsigned gen = (unsigned)(h >> 32);
+    if (slot == 0 || slot > g_slots.size()) return nullptr;
+    if (g_slots[slot - 1].first != gen) return nullptr;
+    Plan *p = g_slots[slot - 1].second;
+    g_slots[slot - 1].second = nullptr;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// device tables
+// ------------------------------------------------------------------------------------------
+struct Builder {
+    Plan *P;
+    int err = FFTB200_SUCCESS;
+    std::map<std::pair<int, long long>, void *> cache;  // (kind, n) -> device table
+
+    void *upload(const void *host, size_t bytes) {
+        void *d = nullptr;
+        if (cudaMalloc(&d, bytes) != cudaSuccess) { err = FFTB200_ALLOC_FAILED; cudaGetLastError(); return nullptr; }
+        P->dev_allocs.push_back(d);
+        if (cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { err = FFTB200_SETUP_FAILED; cudaGetLastError(); return nullptr; }
+        return d;
+    }
+
+    // w_n^k for k in [0, count), in the plan's precision (kind 0) or always fp64 (kind 1)
+    void *table(long long n, long long count, bool force_double, long long step = 1) {
+        const int kind = (force_double ? 1 : 0) + (step != 1 ? 2 : 0);
+        auto key = std::make_pair(kind * 4 + (count == n ? 0 : 1), n * 64 + (step % 64));
+        if (step == 1) {
+            auto it = cache.find(key);
+            if (it != cache.end()) return it->second;
+        }
+        void *d = nullptr;
+        if (P->prec == 1 || force_double) {
+            std::vector<double> h(2 * (size_t)count);
+            for (long long k = 0; k < count; ++k) twiddle((k * step) % n, n, &h[2 * k], &h[2 * k + 1]);
+            d = upload(h.data(), h.size() * sizeof(double));
+        } else {
+            std::vector<float> h(2 * (size_t)count);
+            for (long long k = 0; k < count; ++k) {
+                double re, im;
+                twiddle((k * step) % n, n, &re, &im);
+                h[2 * k] = (float)re;
+                h[2 * k + 1] = (float)im;
+            }
+            d = upload(h.data(), h.size() * sizeof(float));
+        }
+        if (step == 1) cache[key] = d;
+        return d;
+    }
+
+    void *alloc(size_t bytes) {
+        void *d = nullptr;
+        if (cudaMalloc(&d, bytes) != cudaSuccess) { err = FFTB200_ALLOC_FAILED; cudaGetLastError(); return nullptr; }
+        P->dev_allocs.push_back(d);
+        return d;
+    }
+};
+
+static bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+static int ilog2ll(long long v) { int l = 0; while ((1ll << (l + 1)) <= v) ++l; return l; }
+
+struct Level { long long n, is, os; };
+
+// merge adjacent index levels that are dense in both buffers
+static void merge_levels(std::vector<Level> &lv) {
+    std::vector<Level> out;
+    for (const Level &l : lv) {
+        if (l.n == 1) continue;
+        if (!out.empty() && l.is == out.back().n * out.back().is && l.os == out.back().n * out.back().os)
+            out.back().n *= l.n;
+        else
+            out.push_back(l);
+    }
+    lv.swap(out);
+}
+
+static const char *variant_name(int v) {
+    static const char *names[] = {"row", "col", "col+twiddle", "row->col", "r2c-row"};
+    return names[v];
+}
+
+// Add one tile pass.  levels: non-axis index levels, fastest first (levels[0] = lines of a tile).
+static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long long out_ls, std::vector<Level> lv,
+                          int src, int dst, long long twN /* four-step N */, const char *what) {
+    Plan *P = B.P;
+    const TileKernelInfo *ki = find_tile_kernel(P->prec, variant, L);
+    if (!ki) return false;
+    merge_levels(lv);
+    if (lv.size() > 3) return false;
+    while (lv.size() < 3) lv.push_back({1, 0, 0});
+    const bool load_row = (variant == V_RR || variant == V_RC || variant == V_RR_R2C);
+    const bool store_row = (variant == V_RR || variant == V_RR_R2C);
+    if (load_row ? (in_ls != 1) : (lv[0].n > 1 && lv[0].is != 1)) return false;
+    if (store_row ? (out_ls != 1) : (lv[0].n > 1 && lv[0].os != 1)) return false;
+    if (lv[0].n > 0x7fffffffll || lv[1].n > 0x7fffffffll) return false;
+
+    Launch ln;
+    ln.kind = Launch::TILE;
+    ln.ki = ki;
+    ln.src = src;
+    ln.dst = dst;
+    TileParams &tp = ln.tp;
+    tp.tw = (L > ki->R) ? B.table(L, L, false) : nullptr;
+    tp.tw_aux = nullptr;
+    if (variant == V_RR_R2C) tp.tw_aux = B.table(2ll * L, L / 2 + 1, false);
+    tp.tw4_hi = tp.tw4_lo = nullptr;
+    tp.tw4_shift = 0;
+    tp.tw4_mask = 0;
+    if (variant == V_CC_TW) {
+        const int bits = ilog2ll(twN);
+        const int sh = (bits + 1) / 2;
+        tp.tw4_shift = sh;
+        tp.tw4_mask = (1 << sh) - 1;
+        tp.tw4_lo = (const double2 *)B.table(twN, 1ll << sh, true);
+        tp.tw4_hi = (const double2 *)B.table(twN, (twN >> sh) + 1, true, 1ll << sh);
+    }
+    tp.in_ls = in_ls;
+    tp.out_ls = out_ls;
+    tp.n_inner = (int)lv[0].n;
+    tp.in_is = lv[0].is;
+    tp.out_is = lv[0].os;
+    tp.n_o2 = (int)lv[1].n;
+    tp.in_os2 = lv[1].is;
+    tp.out_os2 = lv[1].os;
+    tp.in_os1 = lv[2].is;
+    tp.out_os1 = lv[2].os;
+    tp.tiles_per_outer = (int)((lv[0].n + ki->W - 1) / ki->W);
+    tp.inverse = 0;
+    const long long tiles = (long long)tp.tiles_per_outer * lv[1].n * lv[2].n;
+    if (tiles <= 0 || tiles > 0x7fffffffll) return false;
+    ln.grid = (unsigned)tiles;
+    const long long lines = lv[0].n * lv[1].n * lv[2].n;
+    const size_t ce = P->prec ? 16 : 8;
+    if (variant == V_RR_R2C)
+        ln.algo_bytes = (unsigned long long)lines * ((unsigned long long)L * ce + (unsigned long long)(L + 1) * ce);
+    else
+        ln.algo_bytes = (unsigned long long)lines * L * ce * 2ull;
+    char buf[256];
+    snprintf(buf, sizeof buf, "tile %-11s %s L=%d R=%d W=%d threads=%d smem=%d lines=%lld tiles=%lld (%s)",
+             variant_name(variant), P->prec ? "fp64" : "fp32", L, ki->R, ki->W, ki->threads, ki->smem_bytes, lines,
+             tiles, what);
+    ln.desc = buf;
+    if (ki->smem_bytes > 48 * 1024) {
+        if (cudaFuncSetAttribute((const void *)ki->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ki->smem_bytes) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            B.err = FFTB200_SETUP_FAILED;
+            return false;
+        }
+    }
+    P->launches.push_back(ln);
+    return B.err == FFTB200_SUCCESS;
+}
+
+// split N = 2^k (too long for one tile) into 2 or 3 factors, each tile-friendly
+static std::vector<int> split_1d(long long N, int prec) {
+    const int k = ilog2ll(N);
+    // COL passes want L*W*elt <= 64 KiB with 128-byte segments: L <= 512
+    std::vector<int> f;
+    if (k <= 18) {
+        const int a = k / 2;
+        f = {1 << a, 1 << (k - a)};
+    } else if (k <= 27) {
+        const int a = k / 3, b = (k - a) / 2;
+        f = {1 << a, 1 << b, 1 << (k - a - b)};
+    } else {
+        return f;
+    }
+    (void)prec;
+    return f;
+}
+
+// ------------------------------------------------------------------------------------------
+// fast plan (power-of-two, unit element stride)
+// ------------------------------------------------------------------------------------------
+static bool build_fast(Builder &B) {
+    Plan *P = B.P;
+    const int rank = P->rank;
+    const long long *n = P->n;
+    const int maxL = max_tile_length(P->prec);
+    for (int d = 0; d < rank; ++d)
+        if (!is_pow2(n[d])) return false;
+    if (P->in_stride[rank] != 1 || P->out_stride[rank] != 1) return false;
+    long long total = 1;
+    for (int d = 0; d < rank; ++d) total *= n[d];
+    if (total == 1) return false;  // nothing to transform: generic path copies
+
+    // output extents (last cut to n/2+1 for real input)
+    long long nout[3];
+    for (int d = 0; d < rank; ++d) nout[d] = n[d];
+    const int last = rank - 1;
+    if (P->real) {
+        if (n[last] < 4 || n[last] / 2 > maxL) return false;
+        for (int d = 0; d <= rank; ++d)
+            if (d != rank && (P->in_stride[d] & 1)) return false;  // rows must start on a complex boundary
+        nout[last] = n[last] / 2 + 1;
+    }
+
+    auto levels_for = [&](int axis, bool first_pass) {
+        // fastest first: dims after the axis (reverse), dims before the axis (reverse), batch
+        std::vector<Level> lv;
+        for (int d = rank - 1; d >= 0; --d) {
+            if (d == axis) continue;
+            Level l;
+            l.n = first_pass ? n[d] : nout[d];
+            l.is = first_pass ? P->in_stride[d + 1] : P->out_stride[d + 1];
+            l.os = P->out_stride[d + 1];
+            lv.push_back(l);
+        }
+        Level b;
+        b.n = P->batch;
+        b.is = first_pass ? P->in_stride[0] : P->out_stride[0];
+        b.os = P->out_stride[0];
+        lv.push_back(b);
+        return lv;
+    };
+
+    // ---- last axis (contiguous) ----
+    bool first = true;
+    if (P->real) {
+        std::vector<Level> lv = levels_for(last, true);
+        for (Level &l : lv) l.is /= 2;  // input addressed as packed complex pairs
+        if (!add_tile_pass(B, V_RR_R2C, (int)(n[last] / 2), 1, 1, lv, BUF_IN, BUF_OUT, 0, "axis r2c")) return false;
+        first = false;
+    } else if (n[last] > 1) {
+        if (n[last] <= maxL) {
+            if (!add_tile_pass(B, V_RR, (int)n[last], 1, 1, levels_for(last, true), BUF_IN, BUF_OUT, 0, "last axis"))
+                return false;
+            first = false;
+        } else {
+            // four-step: only as the sole transformed axis of the plan
+            for (int d = 0; d < last; ++d)
+                if (n[d] != 1) return false;
+            std::vector<int> f = split_1d(n[last], P->prec);
+            if (f.empty()) return false;
+            const long long N = n[last];
+            const size_t ce = P->prec ? 16 : 8;
+            P->work_bytes = (size_t)N * P->batch * ce;
+            P->work[0] = B.alloc(P->work_bytes);
+            if (!P->work[0]) return false;
+            const long long bi = P->in_stride[0], bo = P->out_stride[0];
+            if (f.size() == 2) {
+                const long long N1 = f[0], M = f[1];
+                if (!add_tile_pass(B, V_CC_TW, (int)N1, M, M, {{M, 1, 1}, {P->batch, bi, N}}, BUF_IN, BUF_WORK0, N,
+                                   "four-step 1/2"))
+                    return false;
+                if (!add_tile_pass(B, V_RC, (int)M, 1, N1, {{N1, M, 1}, {P->batch, N, bo}}, BUF_WORK0, BUF_OUT, 0,
+                                   "four-step 2/2"))
+                    return false;
+            } else {
+                const long long N1 = f[0], N2 = f[1], N3 = f[2], M = N2 * N3;
+                if (!add_tile_pass(B, V_CC_TW, (int)N1, M, M, {{M, 1, 1}, {P->batch, bi, N}}, BUF_IN, BUF_WORK0, N,
+                                   "six-step 1/3"))
+                    return false;
+                if (!add_tile_pass(B, V_CC_TW, (int)N2, N3, N3, {{N3, 1, 1}, {N1, M, M}, {P->batch, N, N}}, BUF_WORK0,
+                                   BUF_WORK0, M, "six-step 2/3"))
+                    return false;
+                if (!add_tile_pass(B, V_RC, (int)N3, 1, N1 * N2, {{N1, M, 1}, {N2, N3, N1}, {P->batch, N, bo}},
+                                   BUF_WORK0, BUF_OUT, 0, "six-step 3/3"))
+                    return false;
+            }
+            P->inplace_ok = true;  // every pass goes through the work buffer
+            return true;
+        }
+    }
+
+    // ---- remaining axes (strided) ----
+    for (int axis = last - 1; axis >= 0; --axis) {
+        if (n[axis] == 1) continue;
+        if (n[axis] > maxL) return false;
+        std::vector<Level> lv = levels_for(axis, first);
+        const long long in_ls = first ? P->in_stride[axis + 1] : P->out_stride[axis + 1];
+        const long long out_ls = P->out_stride[axis + 1];
+        if (!add_tile_pass(B, V_CC, (int)n[axis], in_ls, out_ls, lv, first ? BUF_IN : BUF_OUT, BUF_OUT, 0,
+                           "strided axis"))
+            return false;
+        first = false;
+    }
+    if (first) return false;
+    // in place is safe when every pass reads and writes the same addresses tile by tile
+    bool same = !P->real;
+    for (int d = 0; d <= rank; ++d) same = same && (P->in_stride[d] == P->out_stride[d]);
+    P->inplace_ok = same;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic plan
+// ------------------------------------------------------------------------------------------
+static unsigned grid_for(long long total) {
+    long long g = (total + 255) / 256;
+    if (g > 148ll * 64) g = 148ll * 64;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+static bool build_generic(Builder &B) {
+    Plan *P = B.P;
+    const int rank = P->rank;
+    const long long *n = P->n;
+    const size_t ce = P->prec ? 16 : 8;
+    long long total_in = P->batch;
+    for (int d = 0; d < rank; ++d) total_in *= n[d];
+    P->work_bytes = (size_t)total_in * ce;
+    P->work[0] = B.alloc(P->work_bytes);
+    P->work[1] = B.alloc(P->work_bytes);
+    if (!P->work[0] || !P->work[1]) return false;
+    P->generic = true;
+    P->inplace_ok = true;
+
+    Launch g;
+    g.kind = Launch::GEN_GATHER;
+    g.real_in = P->real;
+    g.lay.nd = rank + 1;
+    g.lay.n[0] = P->batch;
+    g.lay.stride[0] = P->in_stride[0];
+    for (int d = 0; d < rank; ++d) { g.lay.n[d + 1] = n[d]; g.lay.stride[d + 1] = P->in_stride[d + 1]; }
+    g.total = total_in;
+    g.src = BUF_IN;
+    g.dst = BUF_WORK0;
+    g.grid = grid_for(total_in);
+    g.algo_bytes = (unsigned long long)total_in * (P->elt_in() + ce);
+    g.desc = "generic gather (user layout -> packed complex)";
+    P->launches.push_back(g);
+
+    int cur = BUF_WORK0;
+    long long dims[3];
+    for (int d = 0; d < rank; ++d) dims[d] = n[d];
+    for (int axis = rank - 1; axis >= 0; --axis) {
+        const int L = (int)dims[axis];
+        long long outer = P->batch, inner = 1;
+        for (int d = 0; d < axis; ++d) outer *= dims[d];
+        for (int d = axis + 1; d < rank; ++d) inner *= dims[d];
+        if (L > 1) {
+            const double2 *tw = (const double2 *)B.table(L, L, true);
+            int rem = L, Ns = 1;
+            for (int p = 2; rem > 1; ++p) {
+                if ((long long)p * p > rem) p = rem;
+                while (rem % p == 0) {
+                    Launch s;
+                    s.kind = Launch::GEN_STAGE;
+                    s.outer = outer;
+                    s.inner = inner;
+                    s.L = L;
+                    s.p = p;
+                    s.Ns = Ns;
+                    s.gtw = tw;
+                    s.src = cur;
+                    s.dst = (cur == BUF_WORK0) ? BUF_WORK1 : BUF_WORK0;
+                    s.total = outer * L * inner;
+                    s.grid = grid_for(s.total);
+                    s.algo_bytes = (unsigned long long)s.total * ce * 2ull;
+                    char buf[160];
+                    snprintf(buf, sizeof buf, "generic stage axis=%d L=%d radix=%d Ns=%d lines=%lld", axis, L, p, Ns,
+                             outer * inner);
+                    s.desc = buf;
+                    P->launches.push_back(s);
+                    cur = s.dst;
+                    Ns *= p;
+                    rem /= p;
+                }
+            }
+        }
+        if (P->real && axis == rank - 1) {
+            Launch t;
+            t.kind = Launch::GEN_TRUNC;
+            t.outer = outer;  // lines (inner == 1 on the last axis)
+            t.L = L;
+            t.Lc = L / 2 + 1;
+            t.src = cur;
+            t.dst = (cur == BUF_WORK0) ? BUF_WORK1 : BUF_WORK0;
+            t.total = outer * t.Lc;
+            t.grid = grid_for(t.total);
+            t.algo_bytes = (unsigned long long)t.total * ce * 2ull;
+            t.desc = "generic truncate to n/2+1";
+            P->launches.push_back(t);
+            cur = t.dst;
+            dims[axis] = t.Lc;
+        }
+    }
+    Launch s;
+    s.kind = Launch::GEN_SCATTER;
+    s.lay.nd = rank + 1;
+    s.lay.n[0] = P->batch;
+    s.lay.stride[0] = P->out_stride[0];
+    long long total_out = P->batch;
+    for (int d = 0; d < rank; ++d) { s.lay.n[d + 1] = dims[d]; s.lay.stride[d + 1] = P->out_stride[d + 1]; total_out *= dims[d]; }
+    s.total = total_out;
+    s.src = cur;
+    s.dst = BUF_OUT;
+    s.grid = grid_for(total_out);
+    s.algo_bytes = (unsigned long long)total_out * ce * 2ull;
+    s.desc = "generic scatter (packed complex -> user layout)";
+    P->launches.push_back(s);
+    return B.err == FFTB200_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------
+// execution
+// ------------------------------------------------------------------------------------------
+template <typename T> static cudaError_t launch_generic(const Launch &ln, const void *src, void *dst, int inverse,
+                                                        cudaStream_t st) {
+    using C = cplx<T>;
+    switch (ln.kind) {
+        case Launch::GEN_GATHER:
+            if (ln.real_in)
+                gen_gather_kernel<T, true><<<ln.grid, 256, 0, st>>>(src, (C *)dst, ln.lay, ln.total, 0);
+            else
+                gen_gather_kernel<T, false><<<ln.grid, 256, 0, st>>>(src, (C *)dst, ln.lay, ln.total, inverse);
+            break;
+        case Launch::GEN_STAGE:
+            gen_stage_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.gtw, ln.outer, ln.L, ln.inner,
+                                                         ln.p, ln.Ns);
+            break;
+        case Launch::GEN_TRUNC:
+            gen_truncate_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.outer, ln.L, ln.Lc);
+            break;
+        case Launch::GEN_SCATTER:
+            gen_scatter_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.lay, ln.total, inverse);
+            break;
+        default: break;
+    }
+    return cudaGetLastError();
+}
+
+static int exec_plan(Plan *P, const void *in, void *out, int direction);
+
+static int exec_fallback(Plan *P, const void *in, void *out, int direction);
+
+static int exec_plan(Plan *P, const void *in, void *out, int direction) {
+    if (!in || !out) return FFTB200_INVALID_VALUE;
+    if (direction != FFTB200_FORWARD && direction != FFTB200_INVERSE) return FFTB200_INVALID_VALUE;
+    if (P->real && direction != FFTB200_FORWARD) return FFTB200_INVALID_VALUE;
+    if (in == out && !P->inplace_ok) return FFTB200_INVALID_VALUE;
+    if (!P->generic) {
+        const size_t a_in = P->real ? 2 * P->elt_in() : P->elt_in();
+        if (((uintptr_t)in % a_in) || ((uintptr_t)out % P->elt_out())) return exec_fallback(P, in, out, direction);
+    }
+    DeviceGuard g(P->device);
+    std::lock_guard<std::mutex> lk(P->mu);
+    const int inverse = (direction == FFTB200_INVERSE) ? 1 : 0;
+    const size_t nl = P->launches.size();
+    if (P->profiling && P->events.size() != nl + 1) {
+        for (cudaEvent_t e : P->events) cudaEventDestroy(e);
+        P->events.assign(nl + 1, nullptr);
+        for (size_t i = 0; i <= nl; ++i)
+            if (cudaEventCreate(&P->events[i]) != cudaSuccess) return FFTB200_INTERNAL_ERROR;
+        P->last_ms.assign(nl, 0.f);
+    }
+    if (P->profiling) cudaEventRecord(P->events[0], P->stream);
+    for (size_t i = 0; i < nl; ++i) {
+        const Launch &ln = P->launches[i];
+        const void *bufs_src[4] = {in, out, P->work[0], P->work[1]};
+        void *bufs_dst[4] = {nullptr, out, P->work[0], P->work[1]};
+        const void *src = bufs_src[ln.src];
+        void *dst = bufs_dst[ln.dst];
+        cudaError_t ce;
+        if (ln.kind == Launch::TILE) {
+            TileParams tp = ln.tp;
+            tp.in = src;
+            tp.out = dst;
+            tp.inverse = inverse;
+            ln.ki->fn<<<ln.grid, ln.ki->threads, ln.ki->smem_bytes, P->stream>>>(tp);
+            ce = cudaGetLastError();
+        } else {
+            ce = P->prec ? launch_generic<double>(ln, src, dst, inverse, P->stream)
+                         : launch_generic<float>(ln, src, dst, inverse, P->stream);
+        }
+        if (ce != cudaSuccess) return FFTB200_EXEC_FAILED;
+        if (P->profiling) cudaEventRecord(P->events[i + 1], P->stream);
+    }
+    return FFTB200_SUCCESS;
+}
+
+static int create_plan(Plan **out, int rank, const long long *n, int batch, const long long *in_stride,
+                       const long long *out_stride, fftb200_type type, bool force_generic);
+
+static int exec_fallback(Plan *P, const void *in, void *out, int direction) {
+    {
+        std::lock_guard<std::mutex> lk(P->mu);
+        if (!P->fallback) {
+            DeviceGuard g(P->device);
+            Plan *fb = nullptr;
+            const int rc = create_plan(&fb, P->rank, P->n, P->batch, P->in_stride, P->out_stride, P->type, true);
+            if (rc != FFTB200_SUCCESS) return rc;
+            P->fallback.reset(fb);
+        }
+        P->fallback->stream = P->stream;
+    }
+    return exec_plan(P->fallback.get(), in, out, direction);
+}
+
+static int create_plan(Plan **out, int rank, const long long *n, int batch, const long long *in_stride,
+                       const long long *out_stride, fftb200_type type, bool force_generic) {
+    std::unique_ptr<Plan> P(new Plan);
+    if (cudaGetDevice(&P->device) != cudaSuccess) { cudaGetLastError(); return FFTB200_SETUP_FAILED; }
+    P->type = type;
+    P->prec = (type == FFTB200_Z2Z || type == FFTB200_D2Z) ? 1 : 0;
+    P->real = (type == FFTB200_R2C || type == FFTB200_D2Z);
+    P->rank = rank;
+    P->batch = batch;
+    for (int d = 0; d < rank; ++d) P->n[d] = n[d];
+    for (int d = 0; d <= rank; ++d) { P->in_stride[d] = in_stride[d]; P->out_stride[d] = out_stride[d]; }
+    Builder B;
+    B.P = P.get();
+    bool ok = false;
+    if (!force_generic) {
+        ok = build_fast(B);
+        if (!ok) {
+            // discard partial fast plan
+            P->launches.clear();
+            for (void *d : P->dev_allocs) cudaFree(d);
+            P->dev_allocs.clear();
+            B.cache.clear();
+            P->work[0] = P->work[1] = nullptr;
+            P->work_bytes = 0;
+            if (B.err != FFTB200_SUCCESS) return B.err;
+        }
+    }
+    if (!ok) ok = build_generic(B);
+    if (!ok) {
+        free_plan_resources(P.get());
+        return B.err != FFTB200_SUCCESS ? B.err : FFTB200_UNSUPPORTED;
+    }
+    *out = P.release();
+    return FFTB200_SUCCESS;
+}
+
+}  // namespace fftb200
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace fftb200;
+
+extern "C" {
+
+int fftb200_plan_many(fftb200_handle *plan, int rank, const int *n, const int *inembed, int istride, int idist,
+                      const int *onembed, int ostride, int odist, fftb200_type type, int batch) {
+    if (!plan) return FFTB200_INVALID_VALUE;
+    *plan = 0;
+    if (!n || rank < 1 || rank > 3 || batch < 1) return FFTB200_INVALID_VALUE;
+    if (type != FFTB200_R2C && type != FFTB200_C2C && type != FFTB200_D2Z && type != FFTB200_Z2Z)
+        return FFTB200_INVALID_TYPE;
+    const bool real = (type == FFTB200_R2C || type == FFTB200_D2Z);
+    long long nn[3] = {1, 1, 1}, ie[3], oe[3];
+    for (int d = 0; d < rank; ++d) {
+        if (n[d] < 1) return FFTB200_INVALID_SIZE;
+        nn[d] = n[d];
+    }
+    long long is = 1, os = 1, id, od;
+    if (!inembed || !onembed) {
+        // cuFFT basic layout: packed, strides/dists ignored
+        for (int d = 0; d < rank; ++d) { ie[d] = nn[d]; oe[d] = nn[d]; }
+        if (real) oe[rank - 1] = nn[rank - 1] / 2 + 1;
+        id = od = 1;
+        for (int d = 0; d < rank; ++d) { id *= ie[d]; od *= oe[d]; }
+    } else {
+        if (istride < 1 || ostride < 1) return FFTB200_INVALID_VALUE;
+        for (int d = 0; d < rank; ++d) {
+            ie[d] = inembed[d];
+            oe[d] = onembed[d];
+            const long long need_o = (real && d == rank - 1) ? nn[d] / 2 + 1 : nn[d];
+            if (d > 0 && (ie[d] < nn[d] || oe[d] < need_o)) return FFTB200_INVALID_VALUE;
+        }
+        is = istride; os = ostride; id = idist; od = odist;
+        if (batch > 1 && (id < 1 || od < 1)) return FFTB200_INVALID_VALUE;
+    }
+    long long in_stride[4], out_stride[4];  // [batch, d0.., d_last]
+    in_stride[rank] = is;
+    out_stride[rank] = os;
+    for (int d = rank - 1; d >= 1; --d) {
+        in_stride[d] = in_stride[d + 1] * ie[d];
+        out_stride[d] = out_stride[d + 1] * oe[d];
+    }
+    in_stride[0] = id;
+    out_stride[0] = od;
+    Plan *P = nullptr;
+    const int rc = create_plan(&P, rank, nn, batch, in_stride, out_stride, type, false);
+    if (rc != FFTB200_SUCCESS) return rc;
+    *plan = register_plan(P);
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_set_stream(fftb200_handle plan, void *cuda_stream) {
+    Plan *P = lookup_plan(plan);
+    if (!P) return FFTB200_INVALID_PLAN;
+    std::lock_guard<std::mutex> lk(P->mu);
+    P->stream = (cudaStream_t)cuda_stream;
+    return FFTB200_SUCCESS;
+}
+
+static int exec_typed(fftb200_handle plan, const void *in, void *out, int direction, fftb200_type want) {
+    Plan *P = lookup_plan(plan);
+    if (!P) return FFTB200_INVALID_PLAN;
+    if (P->type != want) return FFTB200_INVALID_TYPE;
+    return exec_plan(P, in, out, direction);
+}
+
+int fftb200_exec_c2c(fftb200_handle plan, const void *in, void *out, int direction) {
+    return exec_typed(plan, in, out, direction, FFTB200_C2C);
+}
+int fftb200_exec_z2z(fftb200_handle plan, const void *in, void *out, int direction) {
+    return exec_typed(plan, in, out, direction, FFTB200_Z2Z);
+}
+int fftb200_exec_r2c(fftb200_handle plan, const void *in, void *out) {
+    return exec_typed(plan, in, out, FFTB200_FORWARD, FFTB200_R2C);
+}
+int fftb200_exec_d2z(fftb200_handle plan, const void *in, void *out) {
+    return exec_typed(plan, in, out, FFTB200_FORWARD, FFTB200_D2Z);
+}
+
+int fftb200_destroy(fftb200_handle plan) {
+    if (plan == 0) return FFTB200_SUCCESS;  // zero-filled plan regions (src/fft.rg:523-531)
+    Plan *P = unregister_plan(plan);
+    if (!P) return FFTB200_INVALID_PLAN;
+    free_plan_resources(P);
+    delete P;
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_get_work_size(fftb200_handle plan, unsigned long long *bytes) {
+    Plan *P = lookup_plan(plan);
+    if (!P || !bytes) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
+    *bytes = (unsigned long long)P->work_bytes * ((P->work[0] ? 1 : 0) + (P->work[1] ? 1 : 0));
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_get_launch_count(fftb200_handle plan, int *launches) {
+    Plan *P = lookup_plan(plan);
+    if (!P || !launches) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
+    *launches = (int)P->launches.size();
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_describe(fftb200_handle plan, char *buf, int buflen) {
+    Plan *P = lookup_plan(plan);
+    if (!P || !buf || buflen < 1) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
+    std::string s;
+    for (const Launch &l : P->launches) { s += l.desc; s += "\n"; }
+    snprintf(buf, (size_t)buflen, "%s", s.c_str());
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_get_launch_bytes(fftb200_handle plan, int i, unsigned long long *bytes) {
+    Plan *P = lookup_plan(plan);
+    if (!P || !bytes) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
+    if (i < 0 || i >= (int)P->launches.size()) return FFTB200_INVALID_VALUE;
+    *bytes = P->launches[i].algo_bytes;
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_set_profiling(fftb200_handle plan, int on) {
+    Plan *P = lookup_plan(plan);
+    if (!P) return FFTB200_INVALID_PLAN;
+    std::lock_guard<std::mutex> lk(P->mu);
+    P->profiling = on != 0;
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_get_launch_ms(fftb200_handle plan, int i, float *ms) {
+    Plan *P = lookup_plan(plan);
+    if (!P || !ms) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
+    std::lock_guard<std::mutex> lk(P->mu);
+    if (i < 0 || i >= (int)P->launches.size() || P->events.size() != P->launches.size() + 1)
+        return FFTB200_INVALID_VALUE;
+    DeviceGuard g(P->device);
+    if (cudaEventSynchronize(P->events[i + 1]) != cudaSuccess) { cudaGetLastError(); return FFTB200_EXEC_FAILED; }
+    if (cudaEventElapsedTime(ms, P->events[i], P->events[i + 1]) != cudaSuccess) { cudaGetLastError(); return FFTB200_EXEC_FAILED; }
+    return FFTB200_SUCCESS;
+}
+
+const char *fftb200_strerror(int code) {
+    switch (code) {
+        case FFTB200_SUCCESS: return "success";
+        case FFTB200_INVALID_PLAN: return "invalid plan handle";
+        case FFTB200_ALLOC_FAILED: return "device allocation failed";
+        case FFTB200_INVALID_TYPE: return "transform type does not match the plan";
+        case FFTB200_INVALID_VALUE: return "invalid argument";
+        case FFTB200_INTERNAL_ERROR: return "internal error";
+        case FFTB200_EXEC_FAILED: return "kernel launch failed";
+        case FFTB200_SETUP_FAILED: return "CUDA setup failed (no device / context?)";
+        case FFTB200_INVALID_SIZE: return "invalid transform size";
+        case FFTB200_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown error";
+    }
+}
+
+int fftb200_version(void) { return 100; }
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// generic_kernels.cuh — any-length, any-layout path (global-memory Stockham, naive radix-p).
+//
+// Covers what the tiled power-of-two kernels do not: prime factors other than 2 (the
+// reference's own test shapes are 3, 5, {3,2,2}, {3,3,2}: test/fft_test.rg:143,247,328,349),
+// element strides != 1, and misaligned base pointers.  It is a CUDA path like the others
+// (no CPU fallback), just not a roofline one: O(L * sum of prime factors) work per line.
+//
+// Data is first gathered into a packed [outer][L][inner] complex work buffer, every prime
+// factor p of L is one ping-pong stage
+//     y[(j/Ns)*Ns*p + j%Ns + q*Ns] = sum_t x[j + t*L/p] * w_L^(t * ((j%Ns)*L/(Ns*p) + q*L/p))
+// (twiddle and p-point DFT merged into one table lookup per term; fp64 table and fp64
+// accumulation for both precisions), and the result is scattered to the caller's layout.
+// Same definitions as the fast path: fftw-3.3.8/doc/reference.texi:1863-1894, dft/generic.c.
+#pragma once
+#include "butterfly.cuh"
+
+namespace fftb200 {
+
+struct GenLayout {
+    int nd;               // number of index levels (batch first), <= 4
+    long long n[4];       // extents, slowest first
+    long long stride[4];  // element strides in the user's buffer
+};
+
+// user buffer (real or complex, any strides) -> packed complex
+template <typename T, bool REAL_IN>
+__global__ void gen_gather_kernel(const void *__restrict__ in, cplx<T> *__restrict__ packed, GenLayout lay,
+                                  long long total, int swap_reim) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        long long rem = e, off = 0;
+#pragma unroll
+        for (int d = 3; d >= 0; --d) {
+            if (d < lay.nd) {
+                const long long q = rem / lay.n[d];
+                off += (rem - q * lay.n[d]) * lay.stride[d];
+                rem = q;
+            }
+        }
+        cplx<T> x;
+        if constexpr (REAL_IN) {
+            x.x = reinterpret_cast<const T *>(in)[off];
+            x.y = (T)0;
+        } else {
+            x = reinterpret_cast<const cplx<T> *>(in)[off];
+        }
+        if (swap_reim) { T s = x.x; x.x = x.y; x.y = s; }
+        packed[e] = x;
+    }
+}
+
+// packed complex -> user buffer (complex, any strides)
+template <typename T>
+__global__ void gen_scatter_kernel(const cplx<T> *__restrict__ packed, cplx<T> *__restrict__ out, GenLayout lay,
+                                   long long total, int swap_reim) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        long long rem = e, off = 0;
+#pragma unroll
+        for (int d = 3; d >= 0; --d) {
+            if (d < lay.nd) {
+                const long long q = rem / lay.n[d];
+                off += (rem - q * lay.n[d]) * lay.stride[d];
+                rem = q;
+            }
+        }
+        cplx<T> x = packed[e];
+        if (swap_reim) { T s = x.x; x.x = x.y; x.y = s; }
+        out[off] = x;
+    }
+}
+
+// one radix-p stage along the middle index of packed [outer][L][inner]
+template <typename T>
+__global__ void gen_stage_kernel(const cplx<T> *__restrict__ x, cplx<T> *__restrict__ y,
+                                 const double2 *__restrict__ tw /* w_L^k */, long long outer, int L, long long inner,
+                                 int p, int Ns) {
+    const long long total = outer * (long long)L * inner;
+    const int Lp = L / p;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e % inner;
+        const long long r1 = e / inner;
+        const int jq = (int)(r1 % L);  // enumerates (j, q): j = jq % Lp, q = jq / Lp
+        const long long o = r1 / L;
+        const int j = jq % Lp, q = jq / Lp;
+        const int k = j % Ns;
+        // exponent step c = k*L/(Ns*p) + q*L/p  (mod L)
+        const long long c = ((long long)k * (L / (Ns * p)) + (long long)q * Lp) % L;
+        const cplx<T> *src = x + (o * L + j) * inner + i;
+        double sr = 0.0, si = 0.0;
+        long long ex = 0;
+        for (int t = 0; t < p; ++t) {
+            const cplx<T> a = src[(long long)t * Lp * inner];
+            const double2 w = __ldg(tw + ex);
+            sr += (double)a.x * w.x - (double)a.y * w.y;
+            si += (double)a.x * w.y + (double)a.y * w.x;
+            ex += c;
+            if (ex >= L) ex -= L;
+        }
+        const long long j0 = (long long)(j / Ns) * Ns * p + k;
+        cplx<T> r;
+        r.x = (T)sr;
+        r.y = (T)si;
+        y[(o * L + j0 + (long long)q * Ns) * inner + i] = r;
+    }
+}
+
+// keep the first Lc of every L-long line: packed [lines][L] -> packed [lines][Lc]
+template <typename T>
+__global__ void gen_truncate_kernel(const cplx<T> *__restrict__ x, cplx<T> *__restrict__ y, long long lines, int L,
+                                    int Lc) {
+    const long long total = lines * Lc;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long ln = e / Lc;
+        const int k = (int)(e - ln * Lc);
+        y[e] = x[ln * L + k];
+    }
+}
+
+}  // namespace fftb200

@@ -1,0 +1,6 @@
+// generated list of instantiations: precision double, variant V_RR_R2C (see tile_inst.inc)
+#define TT double
+#define TT_IS_DOUBLE 1
+#define VAR V_RR_R2C
+#define TABLE_NAME tile_table_f64_r2c
+#include "tile_inst.inc"

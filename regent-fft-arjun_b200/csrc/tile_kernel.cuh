@@ -1,0 +1,278 @@
+// tile_kernel.cuh — the shared-memory Stockham pass: one kernel = one HBM round trip over one axis.
+//
+// A pass transforms a batch of length-L lines (L = 2^k).  A CTA owns a TILE of W lines that are
+// adjacent in the "inner" index; the tile (L x W complex) lives in shared memory between radix
+// stages, every thread keeps R points in registers and runs radix-R butterflies
+// (butterfly.cuh), and each point crosses HBM exactly once in and once out.
+//
+// Addressing (elements): in[o1*in_os1 + o2*in_os2 + i*in_is + l*in_ls], same for out.
+//   ROW access  (x_ls == 1): lanes run along l  -> a warp touches one contiguous run of a line
+//   COL access  (x_is == 1): lanes run along i  -> W*sizeof(complex) = 128 B segments per l
+// Load and store sides choose independently, so a pass can also transpose (four-step 1-D).
+//
+// Stage algebra (decimation in frequency, index digits):  L = r_1 r_2 ... r_S, r_1..r_{S-1} = R,
+// m_s = L / (r_1..r_s).  Stage s runs size-r_s DFTs over digit s, then multiplies by
+// w_{m_{s-1}}^{k_s * lo} (lo = the not-yet-transformed low part), in place at smem position
+// hi*m_{s-1} + d*m_s + lo.  The last stage un-reverses the digits when it computes the output
+// index, so HBM stores are in natural order (autosort) and coalesced.
+//
+// Shared-memory bank conflicts: the linear tile index idx = pos*W + w is XOR-swizzled with the
+// fold of its upper bits (3-bit groups for 16-byte elements, 4-bit groups for 8-byte elements),
+// which makes every access whose lanes differ in 3 (4) consecutive index bits conflict-free,
+// whichever digit the lanes run along.
+//
+// Reference counterpart: the FFTW plan trees of SURVEY.md §8(a9) (dft/ct.c:34-58 Cooley-Tukey,
+// dft/dftw-direct.c:46-56 twiddle codelets, dft/rank-geq2.c:42-52 axis split,
+// rdft/ct-hc2c.c:59-70 r2c post-pass) — here one fused kernel per axis.
+#pragma once
+#include "butterfly.cuh"
+
+namespace fftb200 {
+
+enum TileVariant : int {
+    V_RR = 0,      // ROW load, ROW store                        (contiguous axis)
+    V_CC = 1,      // COL load, COL store                        (strided axis)
+    V_CC_TW = 2,   // COL/COL + multiply by w_N^(i*k) on store   (four-step, first factor)
+    V_RC = 3,      // ROW load, COL store                        (four-step, last factor: transposing)
+    V_RR_R2C = 4,  // ROW load of packed reals, half-length FFT, even/odd post-pass, ROW store
+    V_COUNT = 5
+};
+
+struct TileParams {
+    const void *in;
+    void *out;
+    const void *tw;      // w_L^k, k in [0,L), forward sign, complex<T>
+    const void *tw_aux;  // V_RR_R2C: w_{2L}^k, k in [0, L/2], complex<T>
+    const double2 *tw4_hi;  // V_CC_TW: w_N^(m) = hi[m >> tw4_shift] * lo[m & tw4_mask]
+    const double2 *tw4_lo;
+    long long in_ls, in_is, in_os1, in_os2;
+    long long out_ls, out_is, out_os1, out_os2;
+    int n_inner;   // lines along the inner index
+    int n_o2;      // outer index o = o1*n_o2 + o2
+    int tiles_per_outer;
+    int tw4_shift, tw4_mask;
+    int inverse;   // swap re/im on load and store (backward transform)
+};
+
+constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
+
+template <typename T, int L_, int R_, int W_, int VAR_> struct TileTraits {
+    static constexpr int L = L_, R = R_, W = W_, VAR = VAR_;
+    static constexpr int LOG_L = ilog2c(L), LOG_R = ilog2c(R), LOG_W = ilog2c(W);
+    static constexpr int S = (LOG_L + LOG_R - 1) / LOG_R;          // number of stages
+    static constexpr int R_LAST = L >> (LOG_R * (S - 1));          // radix of the last stage
+    static constexpr int T_LINE = L / R;                            // threads per line
+    static constexpr int LOG_TL = ilog2c(T_LINE);
+    static constexpr int THREADS = T_LINE * W;
+    static constexpr bool LOAD_ROW = (VAR == V_RR || VAR == V_RC || VAR == V_RR_R2C);
+    static constexpr bool STORE_ROW = (VAR == V_RR || VAR == V_RR_R2C);
+    static constexpr bool NEED_SMEM = (S > 1) || (VAR == V_RR_R2C);
+    static constexpr int SMEM_BYTES = NEED_SMEM ? L * W * (int)sizeof(cplx<T>) : 0;
+    // swizzle group width: 8 x 16 B or 16 x 8 B = 128 B = all 32 banks
+    static constexpr int SWZ_BITS = sizeof(cplx<T>) == 16 ? 3 : 4;
+    static_assert(R * T_LINE == L, "R must divide L");
+    static_assert(S == 1 || R_LAST <= R, "bad stage split");
+};
+
+// XOR-fold of x's bits above the low group, in groups of BITS
+template <int BITS, int TOTAL_BITS> __device__ __forceinline__ int swz_fold(int idx) {
+    int f = 0;
+#pragma unroll
+    for (int s = BITS; s < TOTAL_BITS; s += BITS) f ^= (idx >> s);
+    return f & ((1 << BITS) - 1);
+}
+
+template <typename T> __device__ __forceinline__ cplx<T> ld_cplx(const cplx<T> *p) { return __ldg(p); }
+
+template <typename T, int L, int R, int W, int VAR>
+__global__ void __launch_bounds__(TileTraits<T, L, R, W, VAR>::THREADS)
+fft_tile_kernel(const TileParams p) {
+    using TR = TileTraits<T, L, R, W, VAR>;
+    using C = cplx<T>;
+    constexpr int S = TR::S;
+    constexpr int LOG_R = TR::LOG_R, LOG_W = TR::LOG_W, LOG_L = TR::LOG_L;
+    constexpr int T_LINE = TR::T_LINE, LOG_TL = TR::LOG_TL;
+    constexpr int R_LAST = TR::R_LAST;
+    constexpr int IDX_BITS = LOG_L + LOG_W;
+    constexpr int SB = TR::SWZ_BITS;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *sm = reinterpret_cast<C *>(smem_raw);
+
+    const int t = threadIdx.x;
+    // thread -> (line w within tile, slot u within line), for the two access styles
+    const int w_col = t & (W - 1), u_col = t >> LOG_W;
+    const int u_row = t & (T_LINE - 1), w_row = t >> LOG_TL;
+
+    const int tile = blockIdx.x;
+    const int o = tile / p.tiles_per_outer;
+    const int i0 = (tile - o * p.tiles_per_outer) * W;
+    const int o1 = o / p.n_o2, o2 = o - o1 * p.n_o2;
+    const C *__restrict__ gin = reinterpret_cast<const C *>(p.in) + o1 * p.in_os1 + o2 * p.in_os2;
+    C *__restrict__ gout = reinterpret_cast<C *>(p.out) + o1 * p.out_os1 + o2 * p.out_os2;
+    const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);
+    const bool inv = p.inverse != 0;
+
+    C v[R];
+
+    // ------------------------------------------------------------------ stage 1: HBM -> registers
+    const int w1 = TR::LOAD_ROW ? w_row : w_col;
+    const int u1 = TR::LOAD_ROW ? u_row : u_col;
+    {
+        const bool ok = (i0 + w1) < p.n_inner;
+        const C *src = gin + (long long)(i0 + w1) * p.in_is + (long long)u1 * p.in_ls;
+#pragma unroll
+        for (int d = 0; d < R; ++d) {
+            C x = mk<T>((T)0, (T)0);
+            if (ok) x = ld_cplx<T>(src + (long long)(d * T_LINE) * p.in_ls);
+            if (inv) { T s = x.x; x.x = x.y; x.y = s; }
+            v[d] = x;
+        }
+    }
+
+    if constexpr (S > 1) {
+        fft_reg<T, R>(v);
+        // twiddle w_L^(d*u1), then park at position d*m_1 + u1
+        {
+#pragma unroll
+            for (int d = 1; d < R; ++d) v[d] = cmul(v[d], ld_cplx<T>(tw + d * u1));
+            const int base = (u1 << LOG_W) | w1;
+            const int fb = swz_fold<SB, IDX_BITS>(base);
+#pragma unroll
+            for (int d = 0; d < R; ++d) {
+                const int dbits = (d * T_LINE) << LOG_W;
+                sm[(base | dbits) ^ fb ^ swz_fold<SB, IDX_BITS>(dbits)] = v[d];
+            }
+        }
+        __syncthreads();
+
+        // -------------------------------------------------------------- middle stages (radix R)
+#pragma unroll
+        for (int s = 2; s < S; ++s) {
+            // m_s = L / R^s
+            const int log_ms = LOG_L - LOG_R * s;
+            const int ms = 1 << log_ms;
+            const int u = u_col, w = w_col;
+            const int lo = u & (ms - 1);
+            const int hi = u >> log_ms;
+            const int pos = (hi << (log_ms + LOG_R)) | lo;
+            const int base = (pos << LOG_W) | w;
+            const int fb = swz_fold<SB, IDX_BITS>(base);
+#pragma unroll
+            for (int d = 0; d < R; ++d) {
+                const int dbits = (d << log_ms) << LOG_W;
+                v[d] = sm[(base | dbits) ^ fb ^ swz_fold<SB, IDX_BITS>(dbits)];
+            }
+            fft_reg<T, R>(v);
+            // twiddle w_{m_{s-1}}^(d*lo) = w_L^(d*lo*R^(s-1))
+            const int tstep = lo << (LOG_R * (s - 1));
+#pragma unroll
+            for (int d = 1; d < R; ++d) v[d] = cmul(v[d], ld_cplx<T>(tw + d * tstep));
+#pragma unroll
+            for (int d = 0; d < R; ++d) {
+                const int dbits = (d << log_ms) << LOG_W;
+                sm[(base | dbits) ^ fb ^ swz_fold<SB, IDX_BITS>(dbits)] = v[d];
+            }
+            __syncthreads();
+        }
+
+        // -------------------------------------------------------------- last stage: smem -> registers
+        {
+            constexpr int B = R / R_LAST;  // butterflies per thread
+            const int wl = TR::STORE_ROW ? w_row : w_col;
+            const int ul = TR::STORE_ROW ? u_row : u_col;
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int jp = ul + b * T_LINE;  // output-order index of this butterfly, in [0, L/R_LAST)
+                // digits of jp are k_1 (lowest) .. k_{S-1}; position = sum k_i * m_i
+                int pos = 0;
+#pragma unroll
+                for (int i = 1; i < S; ++i) {
+                    const int ki = (jp >> (LOG_R * (i - 1))) & (R - 1);
+                    pos |= ki << (LOG_L - LOG_R * i);
+                }
+                const int base = (pos << LOG_W) | wl;
+                const int fb = swz_fold<SB, IDX_BITS>(base);
+#pragma unroll
+                for (int n = 0; n < R_LAST; ++n) {
+                    const int dbits = n << LOG_W;
+                    v[b * R_LAST + n] = sm[(base | dbits) ^ fb ^ swz_fold<SB, IDX_BITS>(dbits)];
+                }
+                fft_reg<T, R_LAST>(v + b * R_LAST);
+            }
+        }
+    } else {
+        fft_reg<T, R>(v);
+    }
+
+    // After the last stage thread (wl, ul) holds, for b in [0,B) and q in [0,R_LAST):
+    //   X[k],  k = (ul + b*T_LINE) + q*(L/R_LAST),  in v[b*R_LAST + q]
+    constexpr int B = (S > 1) ? R / R_LAST : 1;
+    constexpr int RL = (S > 1) ? R_LAST : R;
+    const int wl = TR::STORE_ROW ? w_row : w_col;
+    const int ul = TR::STORE_ROW ? u_row : u_col;
+
+    if constexpr (VAR == V_RR_R2C) {
+        // ---- even/odd post-pass (cf. rdft/ct-hc2c.c:59-70): the line held L complex = 2L reals.
+        // Z -> smem in natural order, then X[k] = E + w^k O, X[L-k] = conj(E - w^k O),
+        // E = (Z[k] + conj Z[L-k])/2, O = -i (Z[k] - conj Z[L-k])/2, w = w_{2L}.
+        if constexpr (S > 1) __syncthreads();
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+#pragma unroll
+            for (int q = 0; q < RL; ++q) {
+                const int k = (ul + b * T_LINE) + q * (L / RL);
+                const int idx = (k << LOG_W) | wl;
+                sm[idx ^ swz_fold<SB, IDX_BITS>(idx)] = v[b * RL + q];
+            }
+        __syncthreads();
+        const bool ok = (i0 + wl) < p.n_inner;
+        C *dst = gout + (long long)(i0 + wl) * p.out_is;
+        const C *tw2 = reinterpret_cast<const C *>(p.tw_aux);
+        // pairs k in [0, L/2]: thread takes k = ul + j*T_LINE (j < R/2) and, for ul == 0, also k = L/2
+        static_assert(L >= 2 && R >= 2, "r2c fast path needs at least 4 reals per line");
+#pragma unroll
+        for (int j = 0; j <= R / 2; ++j) {
+            const int k = (j < R / 2) ? ul + j * T_LINE : L / 2;
+            if (j == R / 2 && ul != 0) break;
+            const int k2 = (L - k) & (L - 1);  // Z[L] == Z[0]
+            const int ia = (k << LOG_W) | wl, ib = (k2 << LOG_W) | wl;
+            const C a = sm[ia ^ swz_fold<SB, IDX_BITS>(ia)];
+            const C bq = cconj(sm[ib ^ swz_fold<SB, IDX_BITS>(ib)]);
+            const C e = mk<T>((T)0.5 * (a.x + bq.x), (T)0.5 * (a.y + bq.y));
+            const C d = csub(a, bq);
+            const C od = mk<T>((T)0.5 * d.y, (T)-0.5 * d.x);  // -i/2 * (a - b)
+            const C wo = cmul(od, ld_cplx<T>(tw2 + k));
+            if (ok) {
+                dst[(long long)k * p.out_ls] = cadd(e, wo);
+                dst[(long long)(L - k) * p.out_ls] = cconj(csub(e, wo));
+            }
+        }
+        return;
+    } else {
+        const bool ok = (i0 + wl) < p.n_inner;
+        C *dst = gout + (long long)(i0 + wl) * p.out_is;
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+#pragma unroll
+            for (int q = 0; q < RL; ++q) {
+                const int k = (ul + b * T_LINE) + q * (L / RL);
+                C x = v[b * RL + q];
+                if constexpr (VAR == V_CC_TW) {
+                    // four-step twiddle w_N^(i*k), N = L * n_inner; two-level fp64 table
+                    const long long m = (long long)(i0 + wl) * k;
+                    const double2 wh = __ldg(p.tw4_hi + (m >> p.tw4_shift));
+                    const double2 wlw = __ldg(p.tw4_lo + (m & p.tw4_mask));
+                    const double wr = wh.x * wlw.x - wh.y * wlw.y;
+                    const double wi = wh.x * wlw.y + wh.y * wlw.x;
+                    const double xr = (double)x.x * wr - (double)x.y * wi;
+                    const double xi = (double)x.x * wi + (double)x.y * wr;
+                    x.x = (T)xr; x.y = (T)xi;
+                }
+                if (inv) { T s = x.x; x.x = x.y; x.y = s; }
+                if (ok) dst[(long long)k * p.out_ls] = x;
+            }
+    }
+}
+
+}  // namespace fftb200
