@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — the Regent-FFT hot path on B200: 3D C2C complex64 (fp64 parts) 512^3, forward, out of place.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
+         bench.py --gpus N --steps K --warmup W
+
+One "step" = one execute_plan over one 512^3 batch of synthetic input (BASELINE.json configs[3]; metric
+5*N*log2(N)/t, fftw-3.3.8/libbench2/mflops.c:22-23).  N=1: the whole transform on one GPU through
+libfft_b200's C ABI.  N>1: the same 512^3 transform slab-decomposed over N ranks (strong scaling), the
+global transpose fused into the middle FFT pass as peer-to-peer stores over NVLink
+(regent-fft-arjun_b200/distributed.py).
+
+Printed JSON (rank 0, one line):
+  value      whole-job GFLOP/s with the input resident in HBM, CUDA events, max over ranks
+  e2e        same metric through the C ABI with HOST (pinned) in/out buffers: H2D + transform + D2H timed
+  roofline   dominant kernel: algorithmic bytes per launch / mean launch time (events inside the timed
+             region), against the measured HBM copy peak (MEASURED_PEAKS.json, else the recipe's fallback)
+  cpu_baseline  the reference's FFTW 3.3.8 (oracle/_ref, compiled from the vendored sources) on this
+             box's host cores, rank 0, N=1 only, bounded sample
+  --impl reference   times only that FFTW path (all host threads) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SIDE = 512
+SHAPE = (N_SIDE, N_SIDE, N_SIDE)
+N_TOTAL = N_SIDE ** 3
+FLOPS = 5.0 * N_TOTAL * math.log2(N_TOTAL)            # libbench2/mflops.c:22-23
+ELT = 16                                              # complex64 = 2 x fp64
+METRIC = "3D C2C fp64 512^3 GFLOP/s (5NlogN/t)"
+WORKLOAD = "3D C2C complex64 (fp64) 512^3 forward out-of-place, BASELINE configs[3]"
+FALLBACK_HBM_GBS = 6650.0                             # /opt/skills/guides/B200_PROFILING.md
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML; same fields as the recipe's nvidia-smi line)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int, period_s: float = 0.005):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as ex:  # no NVML: report it rather than invent clocks
+            self.err = str(ex)
+        self.period = period_s
+
+    def _names(self, mask):
+        nv = self.nv
+        table = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"),
+                 ("hw_power_brake", "nvmlClocksEventReasonHwPowerBrakeSlowdown", "nvmlClocksThrottleReasonHwPowerBrakeSlowdown")]
+        out = []
+        for name, a, b in table:
+            bit = getattr(nv, a, None) or getattr(nv, b, None)
+            if bit and (mask & bit):
+                out.append(name)
+        return out
+
+    def _loop(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                if get_reasons:
+                    self.reasons.update(self._names(int(get_reasons(self.h))))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.ok:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own FFTW on the host cores
+# ------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def pick_threads(F, all_threads: int) -> int:
+    """FFTW spawns its workers per call; on a many-core host fewer threads than cores can be faster.
+    Probe a 128^3 transform (tens of ms each) at a few counts and keep the fastest."""
+    import numpy as np
+    import oracle
+    x = oracle.synth((128, 128, 128), np.complex128, seed=5)
+    best, best_t = all_threads, None
+    for t in sorted({all_threads, min(all_threads, 64), min(all_threads, 32), min(all_threads, 16)}, reverse=True):
+        times, _ = F.time_transform(x, real=False, threads=t, reps=3, warmup=1)
+        if best_t is None or min(times) < best_t:
+            best, best_t = t, min(times)
+    return best
+
+
+def fftw_engine():
+    """(engine, kind): the reference's FFTW compiled from its vendored sources (kind "reference")."""
+    import oracle
+    if oracle.have_fftw("ref"):
+        return oracle.FFTW.get("ref"), "reference"
+    return None, "port"
+
+
+def time_fftw(steps: int, warmup: int, budget_s: float, threads: int):
+    """Times fftw_plan_dft(3, {512,512,512}, FORWARD, ESTIMATE) + fftw_execute_dft exactly as
+    src/fft.rg:319,608 issue them, with `threads` host threads.  Returns (mean_s, reps_done, sample)."""
+    import numpy as np
+    import oracle
+    F, kind = fftw_engine()
+    x = oracle.synth(SHAPE, np.complex128, seed=4)
+    if F is None:
+        # plain-C port: far slower than FFTW; time one 2-D plane batch and say so
+        sub = x[:4]
+        t0 = time.perf_counter()
+        oracle.port_dft(sub)
+        dt = time.perf_counter() - t0
+        est = dt * (N_SIDE / 4) * (27.0 / 18.0)
+        return est, 1, "oracle port, 4 of 512 planes (2-D part), scaled by planes and log2 ratio", kind, 1
+    threads = pick_threads(F, threads)
+    t_begin = time.perf_counter()
+    # one untimed plan + warm-up execute, then as many timed executes as fit in the budget (<= steps)
+    w_times, _ = F.time_transform(x, real=False, threads=threads, reps=1, warmup=0)
+    t_first = w_times[0]
+    reps = max(1, min(steps, int((budget_s - (time.perf_counter() - t_begin)) / max(t_first, 1e-3))))
+    extra_warm = max(0, min(warmup - 1, int(0.25 * budget_s / max(t_first, 1e-3))))
+    times, _ = F.time_transform(x, real=False, threads=threads, reps=reps, warmup=extra_warm)
+    mean = float(sum(times) / len(times))
+    sample = (f"full 512^3 transform, FFTW 3.3.8 (vendored sources, threads+AVX2), ESTIMATE, {threads} of {host_threads()} host threads (fastest of a 128^3 probe), "
+              f"{1 + extra_warm} warm-up + {reps} timed executes (mean; min {min(times):.3f} s)")
+    return mean, reps, sample, kind, threads
+
+
+def run_reference(args, rank: int) -> int:
+    if rank != 0:
+        return 0
+    threads = host_threads()
+    mean_s, reps, sample, kind, used = time_fftw(args.steps, args.warmup, budget_s=150.0, threads=threads)
+    gf = FLOPS / mean_s / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "engine": "FFTW 3.3.8 CPU path of src/fft.rg:319,608", "timed_executes": reps},
+        "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": used, "kind": kind, "sample": sample},
+        "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel_key: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
+def run_b200(args, rank: int, world: int, local_rank: int) -> int:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libfft_b200 has no CPU path (use --impl reference for FFTW)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    fft = load_package()
+    L = fft._lib
+    L.lib()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps, warmup = args.steps, max(3, args.warmup)
+    stream = torch.cuda.current_stream()
+    g = torch.Generator(device=dev).manual_seed(0x5EED0000 + 4 + rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    if world == 1:
+        x = torch.view_as_complex(torch.rand(*SHAPE, 2, dtype=torch.float64, device=dev, generator=g).sub_(0.5))
+        y = torch.empty_like(x)
+        h = L.plan_many(3, list(SHAPE), None, 0, 0, None, 0, 0, L.Z2Z, 1)
+        L.set_stream(h, stream.cuda_stream)
+        nl = L.launch_count(h)
+        step = lambda: L.execute(h, L.Z2Z, x.data_ptr(), y.data_ptr())
+        launches_per_step = nl
+        parallelism = "single GPU, 3 axis passes"
+        dplan = None
+    else:
+        from regent_fft_arjun_b200 import distributed as D
+        dplan = D.SlabFFT3D(SHAPE, fft.complex64, rank=rank, world=world, device=dev, mode=args.exchange)
+        x = torch.view_as_complex(torch.rand(*dplan.local_in_shape, 2, dtype=torch.float64, device=dev, generator=g).sub_(0.5))
+        dplan.set_input(x)
+        step = dplan.execute
+        launches_per_step = dplan.launches_per_step
+        parallelism = dplan.describe()
+        h = None
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    if h is not None:
+        L.set_profiling(h, True)
+    clocks = ClockSampler(local_rank).start()
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / steps
+    value = FLOPS / (ms_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (events recorded inside the timed region above) -------------
+    peak, peak_src = measured_peak()
+    roof = None
+    passes = []
+    if h is not None:
+        per = [L.launch_ms(h, i) for i in range(nl)]
+        L.set_profiling(h, False)
+        desc = L.describe(h).strip().split("\n")
+        byts = [L.launch_bytes(h, i) for i in range(nl)]
+        top = max(range(nl), key=lambda i: per[i])
+        for i in range(nl):
+            passes.append({"kernel": desc[i].split(" lines=")[0], "ms": round(per[i], 4),
+                           "GB/s": round(byts[i] / per[i] / 1e6, 1), "frac_of_peak": round(byts[i] / per[i] / 1e6 / peak, 4)})
+        ach = byts[top] / per[top] / 1e6
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": ncu_traffic("z2z_512_pass%d" % top), "kernel": desc[top].split(" lines=")[0],
+                "algorithmic_bytes_per_launch": byts[top], "ms_per_launch": per[top], "peak_source": peak_src,
+                "whole_transform": {"pass_model_bytes": sum(byts), "GB/s": sum(byts) / ms_step / 1e6,
+                                    "frac_of_measured_peak": sum(byts) / ms_step / 1e6 / peak,
+                                    "frac_of_nominal_8TBs": sum(byts) / ms_step / 1e6 / 8000.0,
+                                    "strict_min_bytes": 2 * N_TOTAL * ELT,
+                                    "strict_min_GB/s": 2 * N_TOTAL * ELT / ms_step / 1e6},
+                "passes": passes}
+    else:
+        roof = dplan.roofline(ms_step, peak, peak_src)
+
+    # ---- e2e: same metric through the C ABI with HOST buffers (H2D + transform + D2H in the timed region) ----
+    if world == 1:
+        hx = torch.empty(SHAPE, dtype=torch.complex128, pin_memory=True)
+        hy = torch.empty(SHAPE, dtype=torch.complex128, pin_memory=True)
+        hx.copy_(x)
+        e_steps = max(2, min(steps, 5))
+        e2e_step = lambda: L.execute(h, L.Z2Z, hx.data_ptr(), hy.data_ptr())
+        h2d = d2h = N_TOTAL * ELT
+    else:
+        e_steps = max(2, min(steps, 5))
+        e2e_step, h2d, d2h = dplan.make_host_step(x)
+    e2e_step()
+    barrier()
+    e0.record(stream)
+    for _ in range(e_steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+    e_ms /= e_steps
+    e2e = {"value": FLOPS / (e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
+           "d2h_bytes_per_step": d2h * world if world > 1 else d2h, "ms_per_step": e_ms, "steps": e_steps,
+           "host_link_GB/s_each_way": (h2d + d2h) / (e_ms * 1e-3) / 1e9 / 2,
+           "path": "fftb200_exec_z2z(host pinned in, host pinned out): staged H2D, 3 passes on HBM, D2H"}
+    if world == 1:
+        # the device result of the host-buffer call equals the resident-input call on the same data
+        assert torch.equal(hy.to(dev), y), "e2e result differs from the resident-input result"
+
+    # ---- cpu baseline: the reference's FFTW on this box's host cores (rank 0, N=1 only) -----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            mean_s, reps, sample, kind, used = time_fftw(3, 1, budget_s=25.0, threads=host_threads())
+            cpu = {"value": FLOPS / mean_s / 1e9, "unit": "GFLOP/s", "cores": used, "kind": kind, "sample": sample,
+                   "ms_per_transform": mean_s * 1e3}
+        except Exception as ex:  # the baseline is a report, never a dependency of the product number
+            cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+
+    if h is not None:
+        L.destroy(h)
+    if dplan is not None:
+        dplan.destroy()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": parallelism,
+                       "l2": "input+output 4.3 GB per step >> 126 MB L2 (no flush needed)",
+                       "tolerance": "rel-L2 <= 10*log2(N)*eps vs FFTW (tests/test_gpu_parity.py)"},
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches_per_step * steps,
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer stores or NCCL all-to-all")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world == 1 and args.gpus > 1 and args.impl == "b200":
+        # launched without torchrun: re-launch ourselves one rank per GPU
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    return run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -32,6 +32,10 @@
  *   - n[i] is taken as given (the reference passes Regent extents as row-major dims,
  *     src/fft.rg:220-223; the library does not reorder);
  *   - asynchronous with respect to the host, ordered on the plan's stream (default: stream 0);
+ *   - in/out may be device (framebuffer) or host pointers.  Host memory — the zero-copy instances the
+ *     reference's mapper creates (test/test_mapper.cc:45-58), pinned or pageable — is staged through
+ *     plan-owned HBM buffers with one copy in and one copy out on the plan's stream, so every FFT
+ *     pass still runs at HBM speed instead of re-streaming the data over PCIe three times;
  *   - return value 0 == success; 1 and 4 keep cuFFT's meaning so fft.rg's checks
  *     (src/fft.rg:246-250, 584-591) keep working; nothing throws or aborts across the ABI;
  *   - handles are plain 64-bit integers (0 = null) that survive being memcpy'd inside the plan
@@ -106,7 +110,8 @@ FFTB200_API int fftb200_get_launch_count(fftb200_handle plan, int *launches);
 FFTB200_API int fftb200_describe(fftb200_handle plan, char *buf, int buflen);
 /* Algorithmic HBM bytes of launch `i` (elements read * sizeof(in) + elements written * sizeof(out)). */
 FFTB200_API int fftb200_get_launch_bytes(fftb200_handle plan, int i, unsigned long long *bytes);
-/* Record per-launch CUDA events on the next execs (on=1) and read back launch i's last duration. */
+/* Record per-launch CUDA events on the next execs (on=1 starts a new series of up to 256 execs) and
+ * read back launch i's mean duration over the execs recorded since. */
 FFTB200_API int fftb200_set_profiling(fftb200_handle plan, int on);
 FFTB200_API int fftb200_get_launch_ms(fftb200_handle plan, int i, float *ms);
 

@@ -35,8 +35,8 @@ namespace fftb200 {
 // ------------------------------------------------------------------------------------------
 typedef const TileKernelInfo *(*table_fn)(int *);
 static table_fn k_tables[2][V_COUNT] = {
-    {tile_table_f32_rr, tile_table_f32_cc, tile_table_f32_cctw, tile_table_f32_rc, tile_table_f32_r2c},
-    {tile_table_f64_rr, tile_table_f64_cc, tile_table_f64_cctw, tile_table_f64_rc, tile_table_f64_r2c}};
+    {tile_table_f32_rr, tile_table_f32_cc, tile_table_f32_cctw, tile_table_f32_rc, tile_table_f32_r2c, tile_table_f32_ccp},
+    {tile_table_f64_rr, tile_table_f64_cc, tile_table_f64_cctw, tile_table_f64_rc, tile_table_f64_r2c, tile_table_f64_ccp}};
 
 const TileKernelInfo *find_tile_kernel(int prec, int variant, int L) {
     int n = 0;
@@ -90,14 +90,18 @@ struct Launch {
     const double2 *gtw = nullptr;
     bool real_in = false;
     // common
+    long long in_off = 0, out_off = 0;  // element offsets added to the source / destination base (chunked passes)
     int src = BUF_IN, dst = BUF_OUT;
     unsigned grid = 0;
     unsigned long long algo_bytes = 0;
     std::string desc;
 };
 
+struct SlabState;  // slab_plan.inl
+
 struct Plan {
     int device = 0;
+    SlabState *slab = nullptr;  // multi-GPU slab plans only
     cudaStream_t stream = nullptr;
     fftb200_type type = FFTB200_Z2Z;
     int prec = 1;       // 0 fp32, 1 fp64
@@ -109,8 +113,14 @@ struct Plan {
     void *work[2] = {nullptr, nullptr};
     size_t work_bytes = 0;
     bool profiling = false;
-    std::vector<cudaEvent_t> events;
-    std::vector<float> last_ms;
+    // profiling: one row of (launches + 1) events per recorded exec, up to PROF_MAX_EXECS rows
+    std::vector<std::vector<cudaEvent_t>> prof_rows;
+    size_t prof_used = 0;
+    // host-memory staging (zero-copy / pinned / pageable regions, cf. test/test_mapper.cc:45-58):
+    // the transform always runs on HBM; host buffers are copied in and out on the plan's stream
+    void *stage_in = nullptr, *stage_out = nullptr;
+    size_t span_in = 0, span_out = 0;  // bytes from the base pointer to the last touched element + 1
+    bool out_dense = true;             // every byte of the output span is written by the transform
     // saved creation arguments (lazy generic fallback for misaligned pointers)
     int rank = 0, batch = 1;
     long long n[3] = {1, 1, 1};
@@ -136,8 +146,13 @@ static void free_plan_resources(Plan *p) {
     DeviceGuard g(p->device);
     for (void *d : p->dev_allocs) cudaFree(d);
     p->dev_allocs.clear();
-    for (cudaEvent_t e : p->events) cudaEventDestroy(e);
-    p->events.clear();
+    for (auto &row : p->prof_rows)
+        for (cudaEvent_t e : row) cudaEventDestroy(e);
+    p->prof_rows.clear();
+    p->prof_used = 0;
+    if (p->stage_in) cudaFree(p->stage_in);
+    if (p->stage_out) cudaFree(p->stage_out);
+    p->stage_in = p->stage_out = nullptr;
     if (p->fallback) free_plan_resources(p->fallback.get());
 }
 
@@ -250,7 +265,7 @@ static void merge_levels(std::vector<Level> &lv) {
 }
 
 static const char *variant_name(int v) {
-    static const char *names[] = {"row", "col", "col+twiddle", "row->col", "r2c-row"};
+    static const char *names[] = {"row", "col", "col+twiddle", "row->col", "r2c-row", "col->peers"};
     return names[v];
 }
 
@@ -602,27 +617,30 @@ static int exec_plan(Plan *P, const void *in, void *out, int direction);
 
 static int exec_fallback(Plan *P, const void *in, void *out, int direction);
 
-static int exec_plan(Plan *P, const void *in, void *out, int direction) {
-    if (!in || !out) return FFTB200_INVALID_VALUE;
-    if (direction != FFTB200_FORWARD && direction != FFTB200_INVERSE) return FFTB200_INVALID_VALUE;
-    if (P->real && direction != FFTB200_FORWARD) return FFTB200_INVALID_VALUE;
-    if (in == out && !P->inplace_ok) return FFTB200_INVALID_VALUE;
-    if (!P->generic) {
-        const size_t a_in = P->real ? 2 * P->elt_in() : P->elt_in();
-        if (((uintptr_t)in % a_in) || ((uintptr_t)out % P->elt_out())) return exec_fallback(P, in, out, direction);
-    }
-    DeviceGuard g(P->device);
-    std::lock_guard<std::mutex> lk(P->mu);
-    const int inverse = (direction == FFTB200_INVERSE) ? 1 : 0;
+// true when the kernels cannot (or should not) read the pointer directly: pageable host memory is
+// not device-accessible at all, pinned / zero-copy host memory would be re-streamed over PCIe by
+// every pass
+static bool is_host_memory(const void *ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeUnregistered;
+}
+
+static const size_t PROF_MAX_EXECS = 256;
+
+static int run_launches(Plan *P, const void *in, void *out, int inverse) {
     const size_t nl = P->launches.size();
-    if (P->profiling && P->events.size() != nl + 1) {
-        for (cudaEvent_t e : P->events) cudaEventDestroy(e);
-        P->events.assign(nl + 1, nullptr);
-        for (size_t i = 0; i <= nl; ++i)
-            if (cudaEventCreate(&P->events[i]) != cudaSuccess) return FFTB200_INTERNAL_ERROR;
-        P->last_ms.assign(nl, 0.f);
+    std::vector<cudaEvent_t> *row = nullptr;
+    if (P->profiling && P->prof_used < PROF_MAX_EXECS) {
+        if (P->prof_rows.size() <= P->prof_used) {
+            std::vector<cudaEvent_t> r(nl + 1, nullptr);
+            for (size_t i = 0; i <= nl; ++i)
+                if (cudaEventCreate(&r[i]) != cudaSuccess) return FFTB200_INTERNAL_ERROR;
+            P->prof_rows.push_back(r);
+        }
+        row = &P->prof_rows[P->prof_used++];
+        cudaEventRecord((*row)[0], P->stream);
     }
-    if (P->profiling) cudaEventRecord(P->events[0], P->stream);
     for (size_t i = 0; i < nl; ++i) {
         const Launch &ln = P->launches[i];
         const void *bufs_src[4] = {in, out, P->work[0], P->work[1]};
@@ -642,7 +660,50 @@ static int exec_plan(Plan *P, const void *in, void *out, int direction) {
                          : launch_generic<float>(ln, src, dst, inverse, P->stream);
         }
         if (ce != cudaSuccess) return FFTB200_EXEC_FAILED;
-        if (P->profiling) cudaEventRecord(P->events[i + 1], P->stream);
+        if (row) cudaEventRecord((*row)[i + 1], P->stream);
+    }
+    return FFTB200_SUCCESS;
+}
+
+static int exec_plan(Plan *P, const void *in, void *out, int direction) {
+    if (!in || !out) return FFTB200_INVALID_VALUE;
+    if (direction != FFTB200_FORWARD && direction != FFTB200_INVERSE) return FFTB200_INVALID_VALUE;
+    if (P->real && direction != FFTB200_FORWARD) return FFTB200_INVALID_VALUE;
+    if (in == out && !P->inplace_ok) return FFTB200_INVALID_VALUE;
+    const bool host_in = is_host_memory(in), host_out = is_host_memory(out);
+    if (!P->generic && !(host_in && host_out)) {
+        const size_t a_in = P->real ? 2 * P->elt_in() : P->elt_in();
+        if ((!host_in && ((uintptr_t)in % a_in)) || (!host_out && ((uintptr_t)out % P->elt_out())))
+            return exec_fallback(P, in, out, direction);
+    }
+    DeviceGuard g(P->device);
+    std::lock_guard<std::mutex> lk(P->mu);
+    const int inverse = (direction == FFTB200_INVERSE) ? 1 : 0;
+    const void *din = in;
+    void *dout = out;
+    if (host_in) {
+        if (!P->stage_in && cudaMalloc(&P->stage_in, P->span_in) != cudaSuccess) { cudaGetLastError(); return FFTB200_ALLOC_FAILED; }
+        if (cudaMemcpyAsync(P->stage_in, in, P->span_in, cudaMemcpyHostToDevice, P->stream) != cudaSuccess) {
+            cudaGetLastError();
+            return FFTB200_EXEC_FAILED;
+        }
+        din = P->stage_in;
+    }
+    if (host_out) {
+        if (!P->stage_out && cudaMalloc(&P->stage_out, P->span_out) != cudaSuccess) { cudaGetLastError(); return FFTB200_ALLOC_FAILED; }
+        // padding between rows / batches must survive the round trip
+        if (!P->out_dense &&
+            cudaMemcpyAsync(P->stage_out, out, P->span_out, cudaMemcpyHostToDevice, P->stream) != cudaSuccess) {
+            cudaGetLastError();
+            return FFTB200_EXEC_FAILED;
+        }
+        dout = P->stage_out;
+    }
+    const int rc = run_launches(P, din, dout, inverse);
+    if (rc != FFTB200_SUCCESS) return rc;
+    if (host_out && cudaMemcpyAsync(out, P->stage_out, P->span_out, cudaMemcpyDeviceToHost, P->stream) != cudaSuccess) {
+        cudaGetLastError();
+        return FFTB200_EXEC_FAILED;
     }
     return FFTB200_SUCCESS;
 }
@@ -676,6 +737,21 @@ static int create_plan(Plan **out, int rank, const long long *n, int batch, cons
     P->batch = batch;
     for (int d = 0; d < rank; ++d) P->n[d] = n[d];
     for (int d = 0; d <= rank; ++d) { P->in_stride[d] = in_stride[d]; P->out_stride[d] = out_stride[d]; }
+    {
+        long long li = 0, lo = 0, dense = 1;
+        for (int d = 0; d < rank; ++d) {
+            const long long no = (P->real && d == rank - 1) ? n[d] / 2 + 1 : n[d];
+            li += (n[d] - 1) * in_stride[d + 1];
+            lo += (no - 1) * out_stride[d + 1];
+            dense *= no;
+        }
+        li += (long long)(batch - 1) * in_stride[0];
+        lo += (long long)(batch - 1) * out_stride[0];
+        dense *= batch;
+        P->span_in = (size_t)(li + 1) * P->elt_in();
+        P->span_out = (size_t)(lo + 1) * P->elt_out();
+        P->out_dense = (lo + 1 == dense);
+    }
     Builder B;
     B.P = P.get();
     bool ok = false;
@@ -830,18 +906,25 @@ int fftb200_set_profiling(fftb200_handle plan, int on) {
     if (!P) return FFTB200_INVALID_PLAN;
     std::lock_guard<std::mutex> lk(P->mu);
     P->profiling = on != 0;
+    if (on) P->prof_used = 0;  // start a new series; event rows are reused
     return FFTB200_SUCCESS;
 }
 
+// mean duration of launch i over the execs recorded since profiling was switched on
 int fftb200_get_launch_ms(fftb200_handle plan, int i, float *ms) {
     Plan *P = lookup_plan(plan);
     if (!P || !ms) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     std::lock_guard<std::mutex> lk(P->mu);
-    if (i < 0 || i >= (int)P->launches.size() || P->events.size() != P->launches.size() + 1)
-        return FFTB200_INVALID_VALUE;
+    if (i < 0 || i >= (int)P->launches.size() || P->prof_used == 0) return FFTB200_INVALID_VALUE;
     DeviceGuard g(P->device);
-    if (cudaEventSynchronize(P->events[i + 1]) != cudaSuccess) { cudaGetLastError(); return FFTB200_EXEC_FAILED; }
-    if (cudaEventElapsedTime(ms, P->events[i], P->events[i + 1]) != cudaSuccess) { cudaGetLastError(); return FFTB200_EXEC_FAILED; }
+    double sum = 0;
+    for (size_t r = 0; r < P->prof_used; ++r) {
+        float t = 0.f;
+        if (cudaEventSynchronize(P->prof_rows[r][i + 1]) != cudaSuccess) { cudaGetLastError(); return FFTB200_EXEC_FAILED; }
+        if (cudaEventElapsedTime(&t, P->prof_rows[r][i], P->prof_rows[r][i + 1]) != cudaSuccess) { cudaGetLastError(); return FFTB200_EXEC_FAILED; }
+        sum += t;
+    }
+    *ms = (float)(sum / (double)P->prof_used);
     return FFTB200_SUCCESS;
 }
 

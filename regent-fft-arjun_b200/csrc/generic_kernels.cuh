@@ -42,7 +42,10 @@ __global__ void gen_gather_kernel(const void *__restrict__ in, cplx<T> *__restri
             x.x = reinterpret_cast<const T *>(in)[off];
             x.y = (T)0;
         } else {
-            x = reinterpret_cast<const cplx<T> *>(in)[off];
+            // component loads: the user's base may be aligned to sizeof(T) only
+            const T *q = reinterpret_cast<const T *>(in) + 2 * off;
+            x.x = q[0];
+            x.y = q[1];
         }
         if (swap_reim) { T s = x.x; x.x = x.y; x.y = s; }
         packed[e] = x;
@@ -66,7 +69,9 @@ __global__ void gen_scatter_kernel(const cplx<T> *__restrict__ packed, cplx<T> *
         }
         cplx<T> x = packed[e];
         if (swap_reim) { T s = x.x; x.x = x.y; x.y = s; }
-        out[off] = x;
+        T *q = reinterpret_cast<T *>(out) + 2 * off;  // component stores, see gather
+        q[0] = x.x;
+        q[1] = x.y;
     }
 }
 

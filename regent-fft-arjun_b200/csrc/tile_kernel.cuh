@@ -35,8 +35,13 @@ enum TileVariant : int {
     V_CC_TW = 2,   // COL/COL + multiply by w_N^(i*k) on store   (four-step, first factor)
     V_RC = 3,      // ROW load, COL store                        (four-step, last factor: transposing)
     V_RR_R2C = 4,  // ROW load of packed reals, half-length FFT, even/odd post-pass, ROW store
-    V_COUNT = 5
+    V_CC_PEER = 5, // COL/COL, output index k scattered over up to 16 destination buffers: the slab
+                   // exchange fused into the FFT pass (peer GPUs' memory over NVLink, or the blocks of
+                   // a local all-to-all send buffer)
+    V_COUNT = 6
 };
+
+constexpr int MAX_PEERS = 16;
 
 struct TileParams {
     const void *in;
@@ -52,6 +57,10 @@ struct TileParams {
     int tiles_per_outer;
     int tw4_shift, tw4_mask;
     int inverse;   // swap re/im on load and store (backward transform)
+    // V_CC_PEER: output line index k goes to buffer peer[k >> peer_shift] at line (k & peer_mask);
+    // the o1/o2/i offsets and out_ls apply inside that buffer
+    void *peer[MAX_PEERS];
+    int peer_shift, peer_mask;
 };
 
 constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
@@ -270,7 +279,13 @@ fft_tile_kernel(const TileParams p) {
                     x.x = (T)xr; x.y = (T)xi;
                 }
                 if (inv) { T s = x.x; x.x = x.y; x.y = s; }
-                if (ok) dst[(long long)k * p.out_ls] = x;
+                if constexpr (VAR == V_CC_PEER) {
+                    C *pd = reinterpret_cast<C *>(p.peer[k >> p.peer_shift]) + o1 * p.out_os1 + o2 * p.out_os2 +
+                            (long long)(i0 + wl) * p.out_is;
+                    if (ok) pd[(long long)(k & p.peer_mask) * p.out_ls] = x;
+                } else {
+                    if (ok) dst[(long long)k * p.out_ls] = x;
+                }
             }
     }
 }

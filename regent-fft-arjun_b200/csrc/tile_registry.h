@@ -21,10 +21,12 @@ FFTB200_DECL_TABLE(tile_table_f64_cc);
 FFTB200_DECL_TABLE(tile_table_f64_cctw);
 FFTB200_DECL_TABLE(tile_table_f64_rc);
 FFTB200_DECL_TABLE(tile_table_f64_r2c);
+FFTB200_DECL_TABLE(tile_table_f64_ccp);
 FFTB200_DECL_TABLE(tile_table_f32_rr);
 FFTB200_DECL_TABLE(tile_table_f32_cc);
 FFTB200_DECL_TABLE(tile_table_f32_cctw);
 FFTB200_DECL_TABLE(tile_table_f32_rc);
 FFTB200_DECL_TABLE(tile_table_f32_r2c);
+FFTB200_DECL_TABLE(tile_table_f32_ccp);
 
 }  // namespace fftb200

@@ -1,0 +1,520 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI (ctypes over
+libfft_b200.so) and through the host mirror of fft.generate_fft_interface, against
+
+* the committed golden vectors produced by the reference's own FFTW (tests/golden),
+* the eight known answers of the reference's test program (test/fft_test.rg:138-389),
+* the oracle (reference FFTW from oracle/_ref when it travelled, else the plain-C port) on the same
+  seeded inputs at sizes the oracle finishes in seconds,
+* size-independent properties at BASELINE.json's full sizes (impulse, linearity, time shift, Parseval,
+  Hermitian symmetry, forward->backward round trip: libbench2/verify-lib.c:260-434).
+
+Tolerance (BASELINE.json north_star): relative L2 <= 10*log2(N)*eps of the precision
+(oracle.tolerance).  fp32 results are compared with the fp64 transform of the same fp32 input.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fftw_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def L(fft):
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return fft._lib
+
+
+def _torch_dtype(np_dtype):
+    return torch.from_numpy(np.zeros(1, np_dtype)).dtype
+
+
+def _kinds(L):
+    return {"z2z": (L.Z2Z, np.complex128, np.complex128), "c2c": (L.C2C, np.complex64, np.complex64),
+            "d2z": (L.D2Z, np.float64, np.complex128), "r2c": (L.R2C, np.float32, np.complex64)}
+
+
+def gpu_fft(L, kind, x, shape, batch=1, direction=-1):
+    """basic-layout transform of `batch` packed arrays of `shape` through the C ABI"""
+    ftype, dt_in, dt_out = _kinds(L)[kind]
+    real = kind in ("d2z", "r2c")
+    full = ((batch,) if batch > 1 else ()) + tuple(shape)
+    oshape = full[:-1] + (full[-1] // 2 + 1,) if real else full
+    xd = torch.from_numpy(np.ascontiguousarray(x, dtype=dt_in).reshape(full)).cuda()
+    yd = torch.zeros(oshape, dtype=_torch_dtype(dt_out), device="cuda")
+    h = L.plan_many(len(shape), list(shape), None, 0, 0, None, 0, 0, ftype, batch)
+    try:
+        L.set_stream(h, torch.cuda.current_stream().cuda_stream)
+        L.execute(h, ftype, xd.data_ptr(), yd.data_ptr(), direction)
+        torch.cuda.synchronize()
+        desc = L.describe(h)
+    finally:
+        L.destroy(h)
+    assert np.array_equal(xd.cpu().numpy().ravel(), np.ascontiguousarray(x, dtype=dt_in).ravel()), "input not preserved"
+    return yd.cpu().numpy(), desc
+
+
+def cpu_fft(oracle, kind, x, shape, batch=1):
+    """oracle answer in fp64: the reference's FFTW when oracle/_ref travelled, else the C port"""
+    real = kind in ("d2z", "r2c")
+    full = ((batch,) if batch > 1 else ()) + tuple(shape)
+    x64 = np.ascontiguousarray(x).reshape(full).astype(np.float64 if real else np.complex128)
+    F = oracle.FFTW.get("ref") if oracle.have_fftw("ref") else None
+    outs = []
+    for b in range(batch):
+        xb = x64[b] if batch > 1 else x64
+        if F is not None:
+            outs.append(F.r2c(xb) if real else F.dft(xb))
+        else:
+            outs.append(oracle.port_r2c(xb) if real else oracle.port_dft(xb))
+    return np.stack(outs) if batch > 1 else outs[0]
+
+
+# ------------------------------------------------------------------------------------------
+# golden vectors and known answers
+# ------------------------------------------------------------------------------------------
+def test_golden_vectors_fp64(L, oracle):
+    g = np.load(GOLDEN)
+    names = sorted({k[:-3] for k in g.files})
+    assert len(names) >= 20
+    for name in names:
+        x, y = g[name + "__x"], g[name + "__y"]
+        if name.startswith("batch"):
+            ftype = L.Z2Z if name.startswith("batch_c") else L.D2Z
+            xd = torch.from_numpy(x).cuda()
+            yd = torch.zeros(18, dtype=torch.complex128, device="cuda")
+            h = L.plan_many(2, [3, 3], [3, 3], 1, 9, [3, 3], 1, 9, ftype, 2)       # src/fft.rg:389-398
+            L.execute(h, ftype, xd.data_ptr(), yd.data_ptr())
+            torch.cuda.synchronize()
+            L.destroy(h)
+            got = yd.cpu().numpy()
+        else:
+            kind = "z2z" if x.dtype.kind == "c" else "d2z"
+            got, _ = gpu_fft(L, kind, x, x.shape)
+        err = oracle.rel_l2(got, y)
+        assert err <= oracle.tolerance(x.size, single=False), (name, err)
+
+
+def test_golden_vectors_fp32(L, oracle):
+    """the same fixtures rounded to fp32: complex32 / float paths (the reference's CPU branch is a
+    no-op for these, src/fft.rg:296-307; its GPU branch is cuFFT C2C)"""
+    g = np.load(GOLDEN)
+    for name in sorted({k[:-3] for k in g.files}):
+        if name.startswith("batch"):
+            continue
+        x = g[name + "__x"]
+        kind = "c2c" if x.dtype.kind == "c" else "r2c"
+        x32 = x.astype(np.complex64 if kind == "c2c" else np.float32)
+        got, _ = gpu_fft(L, kind, x32, x.shape)
+        want = cpu_fft(oracle, kind, x32, x.shape)
+        err = oracle.rel_l2(got, want)
+        assert err <= oracle.tolerance(x.size, single=True), (name, err)
+
+
+def _run_iface(fft, iface, extent, fill, out_fill=0, batch=False):
+    r = fft.Region(extent, iface.dtype_in).fill(fill)
+    s = fft.Region(extent, iface.dtype_out).fill(out_fill)
+    p = fft.PlanRegion(1)
+    (iface.make_plan_batch if batch else iface.make_plan)(r, s, p)
+    iface.execute_plan_task(r, s, p)
+    torch.cuda.synchronize()
+    iface.destroy_plan(p)
+    assert int(p.data["b200_p"][0]) == 0
+    return s.numpy()
+
+
+def test_reference_test_program_known_answers(fft, L):
+    """test/fft_test.rg: constant input, plan -> execute -> destroy; SURVEY.md §4 table."""
+    c64, c32, dbl, flt = fft.complex64, fft.complex32, fft.double, fft.float32
+    z = 0
+    # test1d (:242)
+    out = _run_iface(fft, fft.generate_fft_interface(fft.int1d, c64, c64), (5,), 3 + 3j)
+    assert np.allclose(out, [15 + 15j, z, z, z, z], atol=1e-13)
+    # test1d_real (:138): only n/2+1 = 2 entries are written
+    out = _run_iface(fft, fft.generate_fft_interface(fft.int1d, dbl, c64), (3,), 3.0, out_fill=-7)
+    assert np.allclose(out[:2], [9, 0], atol=1e-13) and out[2] == -7
+    # test1d_float (:205): GPU C2C gives [9+9i, 0, 0]
+    out = _run_iface(fft, fft.generate_fft_interface(fft.int1d, c32, c32), (3,), 3 + 3j)
+    assert np.allclose(out, [9 + 9j, z, z], atol=1e-5)
+    # test1d_float_real (:171): the reference's exec is commented out; README.md:16 promises the transform
+    out = _run_iface(fft, fft.generate_fft_interface(fft.int1d, flt, c32), (3,), 3.0, out_fill=-7)
+    assert np.allclose(out[:2], [9, 0], atol=1e-5) and out[2] == -7
+    # test2d (:309): output pre-filled with 1
+    out = _run_iface(fft, fft.generate_fft_interface(fft.int2d, c64, c64), (2, 2), 5 + 5j, out_fill=1)
+    assert np.allclose(out, [20 + 20j, z, z, z], atol=1e-13)
+    # test3d (:326)
+    out = _run_iface(fft, fft.generate_fft_interface(fft.int3d, c64, c64), (3, 2, 2), 3 + 3j)
+    assert np.allclose(out, [36 + 36j] + [z] * 11, atol=1e-13)
+    # test3d_batch (:347): 27+27i at flat offsets 0 and 9
+    out = _run_iface(fft, fft.generate_fft_interface(fft.int3d, c64, c64), (3, 3, 2), 3 + 3j, batch=True)
+    want = np.zeros(18, np.complex128)
+    want[0] = want[9] = 27 + 27j
+    assert np.allclose(out, want, atol=1e-13)
+    # test3d_batch_real (:372): row pitch stays 3; entries 2,5,8,11,14,17 untouched
+    out = _run_iface(fft, fft.generate_fft_interface(fft.int3d, dbl, c64), (3, 3, 2), 3.0, out_fill=-7 - 7j, batch=True)
+    for i in (2, 5, 8, 11, 14, 17):
+        assert out[i] == -7 - 7j
+    assert abs(out[0] - 27) < 1e-13 and abs(out[9] - 27) < 1e-13
+    mask = np.ones(18, bool)
+    mask[[0, 9, 2, 5, 8, 11, 14, 17]] = False
+    assert np.allclose(out[mask], 0, atol=1e-13)
+
+
+def test_distrib_known_answer_single_node(fft, L):
+    """test1d_distrib (:282): n nodes x 3, 4+4i -> each shard [12+12i, 0, 0]; one node here."""
+    iface = fft.generate_fft_interface(fft.int1d, fft.complex64, fft.complex64)
+    n = iface.get_num_nodes()
+    r = fft.Region((3 * n,), fft.complex64).fill(4 + 4j)
+    s = fft.Region((3 * n,), fft.complex64)
+    p = fft.PlanRegion(n)
+    rp, sp, pp = r.partition_equal(n), s.partition_equal(n), p.partition_equal(n)
+    iface.make_plan_distrib(r, rp, s, sp, p, pp)
+    for i in range(n):
+        iface.execute_plan_task(rp[i], sp[i], p)
+    torch.cuda.synchronize()
+    iface.destroy_plan_distrib(p, pp)
+    assert np.allclose(s.numpy().reshape(n, 3), [[12 + 12j, 0, 0]] * n, atol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------
+# oracle sweeps
+# ------------------------------------------------------------------------------------------
+POW2 = [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]
+
+
+@pytest.mark.parametrize("kind", ["z2z", "c2c", "d2z", "r2c"])
+def test_every_power_of_two_axis_kernel(L, oracle, kind):
+    sizes = POW2 + {"z2z": [], "c2c": [16384], "d2z": [16384], "r2c": [16384, 32768]}[kind]
+    _, dt_in, _ = _kinds(L)[kind]
+    for i, n in enumerate(sizes):
+        x = oracle.synth((3, n), dt_in, 300 + i)
+        got, desc = gpu_fft(L, kind, x, (n,), batch=3)
+        err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, (n,), batch=3))
+        assert err <= oracle.tolerance(n, kind in ("c2c", "r2c")), (kind, n, err)
+        if n >= 4:
+            assert "generic" not in desc, (kind, n, desc)   # powers of two take the smem Stockham path
+
+
+SHAPES = [((64, 64), 1), ((32, 256), 2), ((256, 32), 1), ((16, 8, 32), 1), ((64, 64, 64), 1), ((128, 4, 512), 1),
+          ((8, 1024, 4), 1), ((1, 64, 1), 1), ((2, 2), 1), ((4, 4, 4), 5),
+          ((3,), 1), ((5,), 2), ((12,), 1), ((1021,), 1), ((3, 2, 2), 1), ((6, 10, 9), 2), ((7, 16), 1), ((1,), 1),
+          ((1 << 15,), 1), ((1 << 18,), 2), ((1 << 20,), 1), ((1 << 22,), 1)]
+
+
+@pytest.mark.parametrize("kind", ["z2z", "c2c", "d2z", "r2c"])
+def test_shapes_against_oracle(L, oracle, kind):
+    _, dt_in, _ = _kinds(L)[kind]
+    for i, (shape, batch) in enumerate(SHAPES):
+        if kind in ("d2z", "r2c") and int(np.prod(shape)) > (1 << 20) and len(shape) == 1:
+            continue
+        full = ((batch,) if batch > 1 else ()) + shape
+        x = oracle.synth(full, dt_in, 400 + i)
+        got, _ = gpu_fft(L, kind, x, shape, batch)
+        err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape, batch))
+        assert err <= oracle.tolerance(int(np.prod(shape)), kind in ("c2c", "r2c")), (kind, shape, batch, err)
+
+
+def test_baseline_config1_n1024(L, oracle):
+    """BASELINE configs[0]: 1D C2C complex64 N=1024 (the reference's CPU-runnable case)."""
+    g = np.load(GOLDEN)
+    x, y = g["c1_1d_c64_1024__x"], g["c1_1d_c64_1024__y"]
+    got, desc = gpu_fft(L, "z2z", x, (1024,))
+    assert oracle.rel_l2(got, y) <= oracle.tolerance(1024, False)
+    assert desc.count("\n") == 1 and "tile" in desc
+
+
+def test_advanced_layout_embeds(L, oracle):
+    """non-NULL embeds: fftw_plan_many_dft semantics (api/plan-many-dft.c:43-46), padded rows and
+    batch distance; complex and real."""
+    n, ie, oe, batch = [8, 16], [10, 20], [9, 24], 3
+    idist, odist = 10 * 20 + 7, 9 * 24 + 5
+    x = oracle.synth((batch * idist,), np.complex128, 500)
+    want = np.full(batch * odist, -1 - 1j, dtype=np.complex128)
+    oracle.port_dft_many(n, batch, x, ie, 1, idist, want, oe, 1, odist)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.full((batch * odist,), -1 - 1j, dtype=torch.complex128, device="cuda")
+    h = L.plan_many(2, n, ie, 1, idist, oe, 1, odist, L.Z2Z, batch)
+    L.execute(h, L.Z2Z, xd.data_ptr(), yd.data_ptr())
+    torch.cuda.synchronize()
+    L.destroy(h)
+    got = yd.cpu().numpy()
+    assert oracle.rel_l2(got, want) <= oracle.tolerance(128, False)
+    assert np.array_equal(got == (-1 - 1j), want == (-1 - 1j))        # padding untouched
+    # strided elements (istride 2 / ostride 3) go through the generic path
+    xs = oracle.synth((2 * 64,), np.complex128, 501)
+    wants = np.zeros(3 * 64, np.complex128)
+    oracle.port_dft_many([64], 1, xs, [64], 2, 0, wants, [64], 3, 0)
+    xd = torch.from_numpy(xs).cuda()
+    yd = torch.zeros(3 * 64, dtype=torch.complex128, device="cuda")
+    h = L.plan_many(1, [64], [64], 2, 0, [64], 3, 0, L.Z2Z, 1)
+    L.execute(h, L.Z2Z, xd.data_ptr(), yd.data_ptr())
+    torch.cuda.synchronize()
+    L.destroy(h)
+    assert oracle.rel_l2(yd.cpu().numpy(), wants) <= oracle.tolerance(64, False)
+    # real, padded
+    xr = oracle.synth((4 * 40,), np.float64, 502)
+    wantr = np.full(4 * 20, 5 + 5j, dtype=np.complex128)
+    oracle.port_r2c_many([32], 4, xr, [36], 1, 40, wantr, [18], 1, 20)
+    xd = torch.from_numpy(xr).cuda()
+    yd = torch.full((4 * 20,), 5 + 5j, dtype=torch.complex128, device="cuda")
+    h = L.plan_many(1, [32], [36], 1, 40, [18], 1, 20, L.D2Z, 4)
+    L.execute(h, L.D2Z, xd.data_ptr(), yd.data_ptr())
+    torch.cuda.synchronize()
+    L.destroy(h)
+    assert oracle.rel_l2(yd.cpu().numpy(), wantr) <= oracle.tolerance(32, False)
+
+
+def test_slab_primitive_batched_2d(L, oracle):
+    """make_plan_batch's call on a power-of-two cube: n[2] batched (n0 x n1) transforms at distance
+    n0*n1 (src/fft.rg:372-398) — the per-slab building block of the slab decomposition."""
+    n0, n1, nb = 64, 128, 6
+    x = oracle.synth((nb, n0, n1), np.complex128, 510)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.zeros_like(xd)
+    h = L.plan_many(2, [n0, n1], [n0, n1], 1, n0 * n1, [n0, n1], 1, n0 * n1, L.Z2Z, nb)
+    assert "generic" not in L.describe(h)
+    L.execute(h, L.Z2Z, xd.data_ptr(), yd.data_ptr())
+    torch.cuda.synchronize()
+    L.destroy(h)
+    want = cpu_fft(oracle, "z2z", x, (n0, n1), batch=nb)
+    assert oracle.rel_l2(yd.cpu().numpy(), want) <= oracle.tolerance(n0 * n1, False)
+
+
+def test_misaligned_pointers_and_inplace(L, oracle):
+    """any naturally aligned pointer is accepted: an 8-byte-aligned complex64 base takes
+    the scalar path; in == out is accepted for C2C."""
+    n = 256
+    x = oracle.synth((n,), np.complex128, 520)
+    buf = torch.zeros(2 * n + 1, dtype=torch.float64, device="cuda")
+    buf[1:] = torch.from_numpy(x.view(np.float64)).cuda()
+    out = torch.zeros(2 * n + 1, dtype=torch.float64, device="cuda")
+    h = L.plan_many(1, [n], None, 0, 0, None, 0, 0, L.Z2Z, 1)
+    L.execute(h, L.Z2Z, buf.data_ptr() + 8, out.data_ptr() + 8)
+    torch.cuda.synchronize()
+    got = out[1:].cpu().numpy().view(np.complex128)
+    assert oracle.rel_l2(got, cpu_fft(oracle, "z2z", x, (n,))) <= oracle.tolerance(n, False)
+    # in place
+    xd = torch.from_numpy(x).cuda()
+    L.execute(h, L.Z2Z, xd.data_ptr(), xd.data_ptr())
+    torch.cuda.synchronize()
+    L.destroy(h)
+    assert oracle.rel_l2(xd.cpu().numpy(), cpu_fft(oracle, "z2z", x, (n,))) <= oracle.tolerance(n, False)
+    # in place, 3-D and four-step
+    for shape in [(32, 16, 64), (1 << 16,)]:
+        x = oracle.synth(shape, np.complex128, 521)
+        xd = torch.from_numpy(x).cuda()
+        h = L.plan_many(len(shape), list(shape), None, 0, 0, None, 0, 0, L.Z2Z, 1)
+        L.execute(h, L.Z2Z, xd.data_ptr(), xd.data_ptr())
+        torch.cuda.synchronize()
+        L.destroy(h)
+        assert oracle.rel_l2(xd.cpu().numpy(), cpu_fft(oracle, "z2z", x, shape)) <= oracle.tolerance(x.size, False)
+
+
+def test_error_codes_on_device(L):
+    h = L.plan_many(1, [64], None, 0, 0, None, 0, 0, L.Z2Z, 1)
+    lib = L.lib()
+    buf = torch.zeros(64, dtype=torch.complex128, device="cuda")
+    assert lib.fftb200_exec_c2c(h, buf.data_ptr(), buf.data_ptr(), -1) == L.INVALID_TYPE   # wrong exec for the plan
+    assert lib.fftb200_exec_z2z(h, None, buf.data_ptr(), -1) == L.INVALID_VALUE
+    assert lib.fftb200_exec_z2z(h, buf.data_ptr(), buf.data_ptr(), 0) == L.INVALID_VALUE   # bad direction
+    assert lib.fftb200_destroy(h) == 0
+    assert lib.fftb200_destroy(h) == L.INVALID_PLAN                                      # double destroy: no crash
+    assert lib.fftb200_exec_z2z(h, buf.data_ptr(), buf.data_ptr(), -1) == L.INVALID_PLAN
+    hr = L.plan_many(1, [64], None, 0, 0, None, 0, 0, L.D2Z, 1)
+    assert lib.fftb200_exec_d2z(hr, buf.data_ptr(), buf.data_ptr()) == L.INVALID_VALUE     # r2c in place unsupported
+    L.destroy(hr)
+
+
+def test_plan_on_user_stream_and_reuse(L, oracle):
+    n = (64, 64)
+    x = oracle.synth((4,) + n, np.complex128, 530)
+    want = cpu_fft(oracle, "z2z", x, n, batch=4)
+    h = L.plan_many(2, list(n), None, 0, 0, None, 0, 0, L.Z2Z, 1)
+    st = torch.cuda.Stream()
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.zeros_like(xd)
+    torch.cuda.synchronize()
+    L.set_stream(h, st.cuda_stream)
+    for b in range(4):                                   # one plan, many executes on new arrays (fftw_execute_dft)
+        L.execute(h, L.Z2Z, xd[b].data_ptr(), yd[b].data_ptr())
+    st.synchronize()
+    L.destroy(h)
+    assert oracle.rel_l2(yd.cpu().numpy(), want) <= oracle.tolerance(64 * 64, False)
+
+
+# ------------------------------------------------------------------------------------------
+# full-size properties (BASELINE configs 2-4 on one GPU); all arithmetic for the checks on the GPU
+# ------------------------------------------------------------------------------------------
+def _rel(a, b):
+    return float((torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b)).item())
+
+
+def _exec(L, h, ftype, x, y, direction=-1):
+    L.execute(h, ftype, x.data_ptr(), y.data_ptr(), direction)
+
+
+def test_c4_512cubed_properties(L, oracle):
+    """3D C2C complex64 512^3: impulse, linearity, time shift, Parseval, round trip."""
+    n = 512
+    N = n ** 3
+    tol = oracle.tolerance(N, False)
+    h = L.plan_many(3, [n, n, n], None, 0, 0, None, 0, 0, L.Z2Z, 1)
+    assert L.launch_count(h) == 3
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    a = torch.rand(n, n, n, 2, dtype=torch.float64, device="cuda", generator=g).sub_(0.5)
+    a = torch.view_as_complex(a)
+    A = torch.empty_like(a)
+    _exec(L, h, L.Z2Z, a, A)
+    torch.cuda.synchronize()
+    # Parseval: sum |A|^2 = N sum |a|^2
+    pa = float(torch.linalg.vector_norm(a).item()) ** 2
+    pA = float(torch.linalg.vector_norm(A).item()) ** 2
+    assert abs(pA / (N * pa) - 1) <= tol
+    # DC bin = sum of the input
+    assert abs(A[0, 0, 0].item() - a.sum().item()) <= tol * abs(a.abs().sum().item())
+    # a sampled bin against the O(N) direct sum
+    k = (37, 401, 255)
+    idx = torch.arange(n, device="cuda", dtype=torch.float64)
+    w = [torch.exp(-2j * torch.pi * ((ki * idx) % n) / n) for ki in k]
+    direct = torch.einsum("abc,a,b,c->", a, w[0], w[1], w[2])
+    assert abs(A[k].item() - direct.item()) <= 4 * tol * float(torch.linalg.vector_norm(a).item())
+    # forward -> backward round trip = N * input (in place on A)
+    B = torch.empty_like(a)
+    _exec(L, h, L.Z2Z, A, B, +1)
+    torch.cuda.synchronize()
+    assert _rel(B / N, a) <= 2 * tol
+    del B
+    # time shift along each axis: F(roll(a, 1, axis))[k] = F(a)[k] * exp(-2 pi i k_axis / n)
+    for axis in range(3):
+        s = torch.roll(a, 1, dims=axis)
+        S = torch.empty_like(a)
+        _exec(L, h, L.Z2Z, s, S)
+        torch.cuda.synchronize()
+        shape = [1, 1, 1]
+        shape[axis] = n
+        ph = torch.exp(-2j * torch.pi * idx / n).reshape(shape)
+        assert _rel(S, A * ph) <= tol, axis
+        del s, S
+    # linearity
+    b = torch.view_as_complex(torch.rand(n, n, n, 2, dtype=torch.float64, device="cuda", generator=g).sub_(0.5))
+    Bf = torch.empty_like(b)
+    _exec(L, h, L.Z2Z, b, Bf)
+    c = 2.5 * a - 1.5j * b
+    C = torch.empty_like(c)
+    _exec(L, h, L.Z2Z, c, C)
+    torch.cuda.synchronize()
+    assert _rel(C, 2.5 * A - 1.5j * Bf) <= tol
+    del b, Bf, c, C
+    # impulse at (1,2,3): |F| = 1 everywhere, phase = product of axis phases
+    e = torch.zeros_like(a)
+    e[1, 2, 3] = 1
+    E = torch.empty_like(a)
+    _exec(L, h, L.Z2Z, e, E)
+    torch.cuda.synchronize()
+    want = (torch.exp(-2j * torch.pi * 1 * idx / n).reshape(n, 1, 1) * torch.exp(-2j * torch.pi * 2 * idx / n).reshape(1, n, 1)
+            * torch.exp(-2j * torch.pi * 3 * idx / n).reshape(1, 1, n))
+    assert _rel(E, want) <= tol
+    L.destroy(h)
+
+
+def test_c4_subcube_against_oracle_128(L, oracle):
+    """the same 3-pass plan shape at 128^3, directly against FFTW"""
+    x = oracle.synth((128, 128, 128), np.complex128, 540)
+    got, desc = gpu_fft(L, "z2z", x, (128, 128, 128))
+    assert oracle.rel_l2(got, cpu_fft(oracle, "z2z", x, (128, 128, 128))) <= oracle.tolerance(128 ** 3, False)
+    assert desc.count("\n") == 3
+
+
+def test_c2_4096sq_r2c_properties(L, oracle):
+    """2D R2C double -> complex64 4096 x 4096: against the complex transform of the same data on the
+    GPU (Hermitian half), Parseval over the half spectrum, DC, plus one row block against FFTW."""
+    n = 4096
+    tol = oracle.tolerance(n * n, False)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    x = torch.rand(n, n, dtype=torch.float64, device="cuda", generator=g).sub_(0.5)
+    y = torch.empty(n, n // 2 + 1, dtype=torch.complex128, device="cuda")
+    h = L.plan_many(2, [n, n], None, 0, 0, None, 0, 0, L.D2Z, 1)
+    assert L.launch_count(h) == 2
+    _exec(L, h, L.D2Z, x, y)
+    hz = L.plan_many(2, [n, n], None, 0, 0, None, 0, 0, L.Z2Z, 1)
+    xc = x.to(torch.complex128)
+    yc = torch.empty_like(xc)
+    _exec(L, hz, L.Z2Z, xc, yc)
+    torch.cuda.synchronize()
+    assert _rel(y, yc[:, : n // 2 + 1]) <= tol
+    # Hermitian symmetry of the full transform: yc[-i, -j] = conj(yc[i, j])
+    flip = torch.roll(torch.flip(yc, dims=(0, 1)), shifts=(1, 1), dims=(0, 1))
+    assert _rel(flip, yc.conj()) <= tol
+    assert abs(y[0, 0].item() - x.sum().item()) <= tol * float(x.abs().sum().item())
+    L.destroy(h)
+    L.destroy(hz)
+    del xc, yc, flip
+    # 1-D batched rows against FFTW: first axis kernel alone
+    rows = x[:8].cpu().numpy()
+    got, _ = gpu_fft(L, "d2z", rows, (n,), batch=8)
+    assert oracle.rel_l2(got, cpu_fft(oracle, "d2z", rows, (n,), batch=8)) <= oracle.tolerance(n, False)
+
+
+def test_c2_small_2d_r2c_against_oracle(L, oracle):
+    x = oracle.synth((512, 512), np.float64, 541)
+    got, _ = gpu_fft(L, "d2z", x, (512, 512))
+    assert oracle.rel_l2(got, cpu_fft(oracle, "d2z", x, (512, 512))) <= oracle.tolerance(512 * 512, False)
+
+
+def test_c3_2pow27_c32_properties(L, oracle):
+    """1D C2C complex32 N = 2^27 (four/six-step): Parseval, sampled bins against a direct fp64 sum,
+    time shift, round trip."""
+    N = 1 << 27
+    tol = oracle.tolerance(N, True)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.view_as_complex(torch.rand(N, 2, dtype=torch.float32, device="cuda", generator=g).sub_(0.5))
+    A = torch.empty_like(a)
+    h = L.plan_many(1, [N], None, 0, 0, None, 0, 0, L.C2C, 1)
+    _exec(L, h, L.C2C, a, A)
+    torch.cuda.synchronize()
+    na = float(torch.linalg.vector_norm(a.to(torch.complex128)).item())
+    nA = float(torch.linalg.vector_norm(A.to(torch.complex128)).item())
+    assert abs(nA * nA / (N * na * na) - 1) <= tol
+    a64 = a.to(torch.complex128)
+    idx = torch.arange(N, device="cuda", dtype=torch.int64)
+    for k in (0, 1, 12345677, N // 2, N - 1):
+        ph = torch.exp(-2j * torch.pi * ((idx * k) % N).to(torch.float64) / N)
+        direct = (a64 * ph).sum().item()
+        assert abs(A[k].item() - direct) <= tol * na, k
+    del a64, idx, ph
+    s = torch.roll(a, 1)
+    S = torch.empty_like(a)
+    _exec(L, h, L.C2C, s, S)
+    torch.cuda.synchronize()
+    phase = torch.exp(-2j * torch.pi * torch.arange(N, device="cuda", dtype=torch.float64) / N).to(torch.complex64)
+    assert _rel((S).to(torch.complex128), (A * phase).to(torch.complex128)) <= tol
+    del s, S, phase
+    B = torch.empty_like(a)
+    _exec(L, h, L.C2C, A, B, +1)
+    torch.cuda.synchronize()
+    assert _rel((B / N).to(torch.complex128), a.to(torch.complex128)) <= 2 * tol
+    L.destroy(h)
+
+
+def test_four_step_against_oracle_2pow22(L, oracle):
+    x = oracle.synth((1 << 22,), np.complex64, 550)
+    got, desc = gpu_fft(L, "c2c", x, (1 << 22,))
+    assert oracle.rel_l2(got, cpu_fft(oracle, "c2c", x, (1 << 22,))) <= oracle.tolerance(1 << 22, True)
+    assert "step" in desc
+
+
+def test_native_library_is_the_one_running(fft, L):
+    """the product path is libfft_b200.so in-tree; the launch list shows hand-written kernels"""
+    assert os.path.samefile(L.LIB_PATH, os.path.join(os.path.dirname(fft.__file__), "libfft_b200.so"))
+    maps = open("/proc/self/maps").read()
+    assert "libfft_b200.so" in maps and "libcufft" not in maps
+    h = L.plan_many(3, [512, 512, 512], None, 0, 0, None, 0, 0, L.Z2Z, 1)
+    assert L.launch_count(h) == 3 and L.work_size(h) == 0
+    total = sum(L.launch_bytes(h, i) for i in range(3))
+    assert total == 3 * 2 * 512 ** 3 * 16                              # pass-model bytes of SURVEY.md §8d
+    L.destroy(h)
