@@ -115,6 +115,38 @@ FFTB200_API int fftb200_get_launch_bytes(fftb200_handle plan, int i, unsigned lo
 FFTB200_API int fftb200_set_profiling(fftb200_handle plan, int on);
 FFTB200_API int fftb200_get_launch_ms(fftb200_handle plan, int i, float *ms);
 
+/* ---- multi-GPU slab transforms (3-D, one plan per GPU / rank) --------------------------------------
+ * No call site in the reference: its distrib path (src/fft.rg:513-537) transforms independent shards
+ * and README.md:117-119 lists a distributed transform as future work.  Semantics follow the vendored
+ * FFTW-MPI (fftw-3.3.8/mpi/dft-rank-geq2.c:40-59, doc/mpi.texi:259-270, 443-466):
+ *   rank r of G holds   in  [n0/G][n1][n2]          slab r of dimension 0, row-major
+ *   and receives        out [n1/G][n0][n2c]         slab r of dimension 1 (FFTW_MPI_TRANSPOSED_OUT),
+ *                                                   n2c = n2 (C2C/Z2Z) or n2/2+1 (R2C/D2Z)
+ * n0, n1, n2 and G are powers of two, G <= 16.  Every rank must make the same sequence of exec calls
+ * (they are collective).  `chunks` = pipeline depth of the fused exchange (1 = no overlap).
+ *
+ * Two ways to run the exchange:
+ *  (1) fused, peer-to-peer: the y-axis FFT pass stores straight into the destination ranks' exchange
+ *      areas over NVLink.  Connect the plans once: across processes exchange the 64-byte IPC handles
+ *      (get_ipc_handle -> any host all-gather -> connect_ipc); inside one process (Legion: one
+ *      process, one GPU processor per device) pass the areas' pointers (get_area -> connect_ptrs).
+ *      Then fftb200_slab_exec.
+ *  (2) staged: exec_pre leaves G packed blocks [d][n0/G][n1/G][n2c] in `send`; the caller runs any
+ *      all-to-all (e.g. NCCL) into `recv`; exec_post finishes from `recv`. */
+FFTB200_API int fftb200_slab_plan(fftb200_handle *plan, const int *n /* [3] */, fftb200_type type, int rank, int nranks,
+                                  int chunks);
+FFTB200_API int fftb200_slab_get_ipc_handle(fftb200_handle plan, void *handle64);
+FFTB200_API int fftb200_slab_connect_ipc(fftb200_handle plan, const void *handles /* nranks x 64 bytes, rank order */);
+FFTB200_API int fftb200_slab_get_area(fftb200_handle plan, void **area, unsigned long long *bytes);
+FFTB200_API int fftb200_slab_connect_ptrs(fftb200_handle plan, void *const *areas /* [nranks] */);
+FFTB200_API int fftb200_slab_exec(fftb200_handle plan, const void *in, void *out, int direction);
+FFTB200_API int fftb200_slab_exec_pre(fftb200_handle plan, const void *in, void *send, int direction);
+FFTB200_API int fftb200_slab_exec_post(fftb200_handle plan, const void *recv, void *out, int direction);
+/* per-phase CUDA-event timing of the last fftb200_slab_exec: ms[0] x-axis pass, ms[1] handshake + y-axis
+ * pass with the exchange, ms[2] remaining z-axis work after the last exchange chunk was issued */
+FFTB200_API int fftb200_slab_set_timing(fftb200_handle plan, int on);
+FFTB200_API int fftb200_slab_get_phase_ms(fftb200_handle plan, float *ms /* [3] */);
+
 FFTB200_API const char *fftb200_strerror(int code);
 /* library version: major*10000 + minor*100 + patch */
 FFTB200_API int fftb200_version(void);

@@ -39,6 +39,16 @@ SYMBOLS = {
     "fftb200_get_launch_bytes": (ctypes.c_int, [_handle, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]),
     "fftb200_set_profiling": (ctypes.c_int, [_handle, ctypes.c_int]),
     "fftb200_get_launch_ms": (ctypes.c_int, [_handle, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
+    "fftb200_slab_plan": (ctypes.c_int, [ctypes.POINTER(_handle), _ip, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "fftb200_slab_get_ipc_handle": (ctypes.c_int, [_handle, _vp]),
+    "fftb200_slab_connect_ipc": (ctypes.c_int, [_handle, _vp]),
+    "fftb200_slab_get_area": (ctypes.c_int, [_handle, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_ulonglong)]),
+    "fftb200_slab_connect_ptrs": (ctypes.c_int, [_handle, ctypes.POINTER(_vp)]),
+    "fftb200_slab_exec": (ctypes.c_int, [_handle, _vp, _vp, ctypes.c_int]),
+    "fftb200_slab_exec_pre": (ctypes.c_int, [_handle, _vp, _vp, ctypes.c_int]),
+    "fftb200_slab_exec_post": (ctypes.c_int, [_handle, _vp, _vp, ctypes.c_int]),
+    "fftb200_slab_set_timing": (ctypes.c_int, [_handle, ctypes.c_int]),
+    "fftb200_slab_get_phase_ms": (ctypes.c_int, [_handle, ctypes.POINTER(ctypes.c_float)]),
     "fftb200_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "fftb200_version": (ctypes.c_int, []),
 }
@@ -143,3 +153,54 @@ def launch_ms(h: int, i: int) -> float:
     ms = ctypes.c_float(0)
     check(lib().fftb200_get_launch_ms(h, i, ctypes.byref(ms)), "fftb200_get_launch_ms")
     return float(ms.value)
+
+
+# ---- multi-GPU slab transforms ---------------------------------------------------------------
+def slab_plan(n, ftype, rank, nranks, chunks=1) -> int:
+    h = _handle(0)
+    check(lib().fftb200_slab_plan(ctypes.byref(h), _ints(n), ftype, rank, nranks, chunks), "fftb200_slab_plan")
+    return int(h.value)
+
+
+def slab_ipc_handle(h: int) -> bytes:
+    buf = ctypes.create_string_buffer(64)
+    check(lib().fftb200_slab_get_ipc_handle(h, buf), "fftb200_slab_get_ipc_handle")
+    return buf.raw
+
+
+def slab_connect_ipc(h: int, handles: bytes) -> None:
+    buf = ctypes.create_string_buffer(handles, len(handles))
+    check(lib().fftb200_slab_connect_ipc(h, buf), "fftb200_slab_connect_ipc")
+
+
+def slab_area(h: int):
+    p, b = _vp(0), ctypes.c_ulonglong(0)
+    check(lib().fftb200_slab_get_area(h, ctypes.byref(p), ctypes.byref(b)), "fftb200_slab_get_area")
+    return int(p.value or 0), int(b.value)
+
+
+def slab_connect_ptrs(h: int, areas) -> None:
+    arr = (_vp * len(areas))(*[_vp(a) for a in areas])
+    check(lib().fftb200_slab_connect_ptrs(h, arr), "fftb200_slab_connect_ptrs")
+
+
+def slab_exec(h: int, in_ptr: int, out_ptr: int, direction: int = FORWARD) -> None:
+    check(lib().fftb200_slab_exec(h, in_ptr, out_ptr, direction), "fftb200_slab_exec")
+
+
+def slab_exec_pre(h: int, in_ptr: int, send_ptr: int, direction: int = FORWARD) -> None:
+    check(lib().fftb200_slab_exec_pre(h, in_ptr, send_ptr, direction), "fftb200_slab_exec_pre")
+
+
+def slab_exec_post(h: int, recv_ptr: int, out_ptr: int, direction: int = FORWARD) -> None:
+    check(lib().fftb200_slab_exec_post(h, recv_ptr, out_ptr, direction), "fftb200_slab_exec_post")
+
+
+def slab_set_timing(h: int, on: bool) -> None:
+    check(lib().fftb200_slab_set_timing(h, 1 if on else 0), "fftb200_slab_set_timing")
+
+
+def slab_phase_ms(h: int):
+    ms = (ctypes.c_float * 3)()
+    check(lib().fftb200_slab_get_phase_ms(h, ms), "fftb200_slab_get_phase_ms")
+    return [float(v) for v in ms]

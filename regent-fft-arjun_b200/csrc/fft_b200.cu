@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -74,6 +75,28 @@ static void twiddle(long long m, long long n, double *re, double *im) {
     if (octant & 4) { s = -s; }
     *re = (double)c;
     *im = (double)(-s);  // forward sign
+}
+
+// one launch of a tile pass; cluster kernels go through cudaLaunchKernelEx with the cluster dimension
+static cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st, const TileParams &tp) {
+    if (ki->cluster <= 1) {
+        ki->fn<<<grid, ki->threads, ki->smem_bytes, st>>>(tp);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid / ki->cluster * ki->cluster, 1, 1);
+    cfg.blockDim = dim3(ki->threads, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)ki->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)ki->cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, ki->fn, tp);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 enum BufSel { BUF_IN = 0, BUF_OUT = 1, BUF_WORK0 = 2, BUF_WORK1 = 3 };
@@ -142,8 +165,11 @@ struct DeviceGuard {
     }
 };
 
+static void slab_free(Plan *p);
+
 static void free_plan_resources(Plan *p) {
     DeviceGuard g(p->device);
+    slab_free(p);
     for (void *d : p->dev_allocs) cudaFree(d);
     p->dev_allocs.clear();
     for (auto &row : p->prof_rows)
@@ -254,8 +280,10 @@ struct Level { long long n, is, os; };
 // merge adjacent index levels that are dense in both buffers
 static void merge_levels(std::vector<Level> &lv) {
     std::vector<Level> out;
-    for (const Level &l : lv) {
-        if (l.n == 1) continue;
+    for (size_t i = 0; i < lv.size(); ++i) {
+        const Level &l = lv[i];
+        // a unit-stride level of extent 1 stays: it is the tile's inner index (ragged last chunk of a slab pass)
+        if (l.n == 1 && !(i == 0 && l.is == 1 && l.os == 1 && lv.size() > 1)) continue;
         if (!out.empty() && l.is == out.back().n * out.back().is && l.os == out.back().n * out.back().os)
             out.back().n *= l.n;
         else
@@ -290,8 +318,9 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     ln.src = src;
     ln.dst = dst;
     TileParams &tp = ln.tp;
-    tp.tw = (L > ki->R) ? B.table(L, L, false) : nullptr;
+    tp.tw = (L > ki->R) ? B.table(L / ki->cluster, L / ki->cluster, false) : nullptr;  // w_LL of the CTA-local stages
     tp.tw_aux = nullptr;
+    if (ki->cluster > 1) tp.tw_aux = B.table(L, L, false);  // cross-CTA stage twiddles w_L
     if (variant == V_RR_R2C) tp.tw_aux = B.table(2ll * L, L / 2 + 1, false);
     tp.tw4_hi = tp.tw4_lo = nullptr;
     tp.tw4_shift = 0;
@@ -318,7 +347,9 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     tp.inverse = 0;
     const long long tiles = (long long)tp.tiles_per_outer * lv[1].n * lv[2].n;
     if (tiles <= 0 || tiles > 0x7fffffffll) return false;
-    ln.grid = (unsigned)tiles;
+    if (tiles * ki->cluster > 0x7fffffffll) return false;
+    ln.grid = (unsigned)(tiles * ki->cluster);
+    tp.n_tiles = (int)tiles;
     const long long lines = lv[0].n * lv[1].n * lv[2].n;
     const size_t ce = P->prec ? 16 : 8;
     if (variant == V_RR_R2C)
@@ -326,9 +357,9 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     else
         ln.algo_bytes = (unsigned long long)lines * L * ce * 2ull;
     char buf[256];
-    snprintf(buf, sizeof buf, "tile %-11s %s L=%d R=%d W=%d threads=%d smem=%d lines=%lld tiles=%lld (%s)",
-             variant_name(variant), P->prec ? "fp64" : "fp32", L, ki->R, ki->W, ki->threads, ki->smem_bytes, lines,
-             tiles, what);
+    snprintf(buf, sizeof buf, "tile %-11s %s L=%d R=%d W=%d threads=%d smem=%d cluster=%d lines=%lld tiles=%lld (%s)",
+             variant_name(variant), P->prec ? "fp64" : "fp32", L, ki->R, ki->W, ki->threads, ki->smem_bytes, ki->cluster,
+             lines, tiles, what);
     ln.desc = buf;
     if (ki->smem_bytes > 48 * 1024) {
         if (cudaFuncSetAttribute((const void *)ki->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ki->smem_bytes) !=
@@ -653,8 +684,7 @@ static int run_launches(Plan *P, const void *in, void *out, int inverse) {
             tp.in = src;
             tp.out = dst;
             tp.inverse = inverse;
-            ln.ki->fn<<<ln.grid, ln.ki->threads, ln.ki->smem_bytes, P->stream>>>(tp);
-            ce = cudaGetLastError();
+            ce = launch_tile(ln.ki, ln.grid, P->stream, tp);
         } else {
             ce = P->prec ? launch_generic<double>(ln, src, dst, inverse, P->stream)
                          : launch_generic<float>(ln, src, dst, inverse, P->stream);
@@ -777,6 +807,8 @@ static int create_plan(Plan **out, int rank, const long long *n, int batch, cons
     return FFTB200_SUCCESS;
 }
 
+#include "slab_plan.inl"
+
 }  // namespace fftb200
 
 // ==========================================================================================
@@ -845,6 +877,7 @@ static int exec_typed(fftb200_handle plan, const void *in, void *out, int direct
     Plan *P = lookup_plan(plan);
     if (!P) return FFTB200_INVALID_PLAN;
     if (P->type != want) return FFTB200_INVALID_TYPE;
+    if (P->slab) return FFTB200_INVALID_PLAN;  // slab plans run through fftb200_slab_exec*
     return exec_plan(P, in, out, direction);
 }
 
@@ -925,6 +958,143 @@ int fftb200_get_launch_ms(fftb200_handle plan, int i, float *ms) {
         sum += t;
     }
     *ms = (float)(sum / (double)P->prof_used);
+    return FFTB200_SUCCESS;
+}
+
+// ---- multi-GPU slab transforms ------------------------------------------------------------
+static Plan *lookup_slab(fftb200_handle plan) {
+    Plan *P = lookup_plan(plan);
+    return (P && P->slab) ? P : nullptr;
+}
+
+static int slab_direction(Plan *P, int direction, int *inverse) {
+    if (direction != FFTB200_FORWARD && direction != FFTB200_INVERSE) return FFTB200_INVALID_VALUE;
+    if (P->real && direction != FFTB200_FORWARD) return FFTB200_INVALID_VALUE;
+    *inverse = direction == FFTB200_INVERSE;
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_slab_plan(fftb200_handle *plan, const int *n, fftb200_type type, int rank, int nranks, int chunks) {
+    if (!plan) return FFTB200_INVALID_VALUE;
+    *plan = 0;
+    if (!n) return FFTB200_INVALID_VALUE;
+    if (type != FFTB200_R2C && type != FFTB200_C2C && type != FFTB200_D2Z && type != FFTB200_Z2Z)
+        return FFTB200_INVALID_TYPE;
+    Plan *P = nullptr;
+    const int rc = slab_create(&P, n, type, rank, nranks, chunks);
+    if (rc != FFTB200_SUCCESS) return rc;
+    *plan = register_plan(P);
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_slab_get_ipc_handle(fftb200_handle plan, void *handle64) {
+    Plan *P = lookup_slab(plan);
+    if (!P || !handle64) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(P->device);
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, P->slab->area) != cudaSuccess) { cudaGetLastError(); return FFTB200_SETUP_FAILED; }
+    memcpy(handle64, &h, 64);
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_slab_connect_ipc(fftb200_handle plan, const void *handles) {
+    Plan *P = lookup_slab(plan);
+    if (!P || !handles) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
+    SlabState *S = P->slab;
+    DeviceGuard g(P->device);
+    std::lock_guard<std::mutex> lk(P->mu);
+    for (int d = 0; d < S->G; ++d) {
+        if (d == S->rank || S->peer_mapped[d]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)d, 64);
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            return FFTB200_SETUP_FAILED;
+        }
+        S->peer_area[d] = ptr;
+        S->peer_mapped[d] = true;
+    }
+    S->connected = true;
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_slab_get_area(fftb200_handle plan, void **area, unsigned long long *bytes) {
+    Plan *P = lookup_slab(plan);
+    if (!P || !area) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
+    *area = P->slab->area;
+    if (bytes) *bytes = P->slab->area_bytes;
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_slab_connect_ptrs(fftb200_handle plan, void *const *areas) {
+    Plan *P = lookup_slab(plan);
+    if (!P || !areas) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
+    SlabState *S = P->slab;
+    DeviceGuard g(P->device);
+    std::lock_guard<std::mutex> lk(P->mu);
+    for (int d = 0; d < S->G; ++d) {
+        if (d == S->rank) continue;
+        if (!areas[d]) return FFTB200_INVALID_VALUE;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, areas[d]) != cudaSuccess) { cudaGetLastError(); return FFTB200_INVALID_VALUE; }
+        if (a.device != P->device) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return FFTB200_SETUP_FAILED; }
+            cudaGetLastError();
+        }
+        S->peer_area[d] = areas[d];
+    }
+    S->connected = true;
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_slab_exec(fftb200_handle plan, const void *in, void *out, int direction) {
+    Plan *P = lookup_slab(plan);
+    if (!P) return FFTB200_INVALID_PLAN;
+    if (!in || !out) return FFTB200_INVALID_VALUE;
+    int inverse = 0;
+    const int rc = slab_direction(P, direction, &inverse);
+    return rc ? rc : slab_exec_p2p(P, in, out, inverse);
+}
+
+int fftb200_slab_exec_pre(fftb200_handle plan, const void *in, void *send, int direction) {
+    Plan *P = lookup_slab(plan);
+    if (!P) return FFTB200_INVALID_PLAN;
+    if (!in || !send) return FFTB200_INVALID_VALUE;
+    int inverse = 0;
+    const int rc = slab_direction(P, direction, &inverse);
+    return rc ? rc : slab_exec_pre(P, in, send, inverse);
+}
+
+int fftb200_slab_exec_post(fftb200_handle plan, const void *recv, void *out, int direction) {
+    Plan *P = lookup_slab(plan);
+    if (!P) return FFTB200_INVALID_PLAN;
+    if (!recv || !out) return FFTB200_INVALID_VALUE;
+    int inverse = 0;
+    const int rc = slab_direction(P, direction, &inverse);
+    return rc ? rc : slab_exec_post(P, recv, out, inverse);
+}
+
+int fftb200_slab_set_timing(fftb200_handle plan, int on) {
+    Plan *P = lookup_slab(plan);
+    if (!P) return FFTB200_INVALID_PLAN;
+    std::lock_guard<std::mutex> lk(P->mu);
+    P->slab->timing = on != 0;
+    return FFTB200_SUCCESS;
+}
+
+// ms[0] = pass 1, ms[1] = wait + pass 2 (all chunks issued), ms[2] = tail until the last pass 3 ends
+int fftb200_slab_get_phase_ms(fftb200_handle plan, float *ms) {
+    Plan *P = lookup_slab(plan);
+    if (!P || !ms) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
+    SlabState *S = P->slab;
+    std::lock_guard<std::mutex> lk(P->mu);
+    DeviceGuard g(P->device);
+    if (cudaEventSynchronize(S->ev_t[3]) != cudaSuccess) { cudaGetLastError(); return FFTB200_INVALID_VALUE; }
+    for (int i = 0; i < 3; ++i)
+        if (cudaEventElapsedTime(&ms[i], S->ev_t[i], S->ev_t[i + 1]) != cudaSuccess) { cudaGetLastError(); return FFTB200_INVALID_VALUE; }
     return FFTB200_SUCCESS;
 }
 

@@ -1,0 +1,305 @@
+// slab_plan.inl — multi-GPU slab decomposition of 3-D transforms (included by fft_b200.cu inside
+// namespace fftb200; it uses the plan builder's internals).
+//
+// No reference counterpart in src/fft.rg (its "distrib" path runs independent shard FFTs,
+// src/fft.rg:513-537; README.md:117-119 lists a distributed transform as future work).  The scheme is
+// the one the vendored FFTW-MPI uses (fftw-3.3.8/mpi/dft-rank-geq2.c:40-59: local FFTs over the
+// non-distributed dims, global transpose, local FFTs over the formerly distributed dim;
+// mpi/transpose-alltoall.c:49-100: pack + all-to-all + unpack; equal blocks, mpi/block.c:39-50), with
+// the output left distributed over dim 1 exactly like FFTW_MPI_TRANSPOSED_OUT (doc/mpi.texi:443-466).
+//
+//   rank r holds   in  [n0/G][n1][n2]      (slab r of dim 0, row-major)
+//   pass 1         x-axis FFT (or fused r2c)              in  -> tmp [n0/G][n1][n2c]     HBM
+//   pass 2         y-axis FFT whose STORE is the exchange: output line index k1 belongs to rank
+//                  k1 / (n1/G); it is written straight into that rank's receive buffer
+//                  recv_d [n1/G][n0][n2c] at [k1 % (n1/G)][r*n0/G + p][i]
+//                    - p2p mode: recv_d is peer memory mapped over NVLink (cudaIpc / peer access); no
+//                      pack, no NCCL, no unpack: the all-to-all IS the FFT pass's store
+//                    - staged mode: recv_d are the G blocks of a local send buffer; the host runs any
+//                      all-to-all (NCCL) on it
+//   pass 3         z-axis FFT                             recv -> out [n1/G][n0][n2c]    HBM
+//
+// p2p mode pipelines passes 2 and 3 over J chunks of the contiguous index i: chunk j of pass 3 starts
+// as soon as every rank has signalled chunk j of pass 2 (flags written into each peer's exchange area),
+// so the z-axis pass hides under the NVLink transfer of the following chunks.
+
+struct SlabState {
+    int rank = 0, G = 1, J = 1;
+    long long n0 = 0, n1 = 0, n2 = 0, n2c = 0, n0l = 0, n1l = 0;
+    void *tmp = nullptr;   // [n0l][n1][n2c]
+    void *area = nullptr;  // exchange area: recv [n1l][n0][n2c], then flags
+    size_t recv_bytes = 0, area_bytes = 0, flags_off = 0;
+    void *peer_area[MAX_PEERS] = {};
+    bool peer_mapped[MAX_PEERS] = {};
+    bool connected = false;
+    unsigned long long epoch = 0;
+    cudaStream_t aux = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;
+    cudaEvent_t ev_done = nullptr, ev_t[5] = {};
+    bool timing = false;
+    int l_pass1 = -1, l_pre2 = -1, l_post3 = -1;
+    std::vector<int> l_pass2, l_pass3;
+    long long chunk_w = 0;
+};
+
+// flags: [kind 0 = "receive buffer free", 1.. = "chunk j written"][source rank] epochs
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct SlabPeers {
+    unsigned long long *flags[MAX_PEERS];
+};
+
+// one thread per destination rank: tell it that this rank's slot (kind, me) reached `epoch`
+__global__ void slab_signal_kernel(SlabPeers peers, int G, int me, int kind, unsigned long long epoch) {
+    __threadfence_system();
+    const int d = threadIdx.x;
+    if (d < G) st_release_sys(peers.flags[d] + (size_t)kind * MAX_PEERS + me, epoch);
+}
+
+// one thread per source rank: wait until its slot (kind, src) in MY flags reached `epoch`
+__global__ void slab_wait_kernel(const unsigned long long *flags, int G, int kind, unsigned long long epoch) {
+    const int s = threadIdx.x;
+    if (s < G) {
+        const unsigned long long *f = flags + (size_t)kind * MAX_PEERS + s;
+        while (ld_acquire_sys(f) < epoch) __nanosleep(200);
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
+static void slab_free(Plan *P) {
+    SlabState *S = P->slab;
+    if (!S) return;
+    for (int d = 0; d < S->G; ++d)
+        if (S->peer_mapped[d] && S->peer_area[d]) cudaIpcCloseMemHandle(S->peer_area[d]);
+    if (S->tmp) cudaFree(S->tmp);
+    if (S->area) cudaFree(S->area);
+    if (S->aux) cudaStreamDestroy(S->aux);
+    for (cudaEvent_t e : S->ev_chunk) cudaEventDestroy(e);
+    if (S->ev_done) cudaEventDestroy(S->ev_done);
+    for (cudaEvent_t e : S->ev_t)
+        if (e) cudaEventDestroy(e);
+    cudaGetLastError();
+    delete S;
+    P->slab = nullptr;
+}
+
+static int slab_launch(Plan *P, int idx, const void *src, void *dst, void *const *peers, int inverse, cudaStream_t st) {
+    const int npeers = P->slab->G;
+    const Launch &ln = P->launches[idx];
+    const size_t ce = P->prec ? 16 : 8;
+    TileParams tp = ln.tp;
+    // the r2c pass addresses its input as packed complex pairs, so in_off is in those units too
+    tp.in = (const char *)src + (size_t)ln.in_off * ce;
+    tp.out = dst ? (char *)dst + (size_t)ln.out_off * ce : nullptr;
+    tp.inverse = inverse;
+    if (peers)
+        for (int d = 0; d < npeers; ++d) tp.peer[d] = (char *)peers[d] + (size_t)ln.out_off * ce;
+    return launch_tile(ln.ki, ln.grid, st, tp) == cudaSuccess ? FFTB200_SUCCESS : FFTB200_EXEC_FAILED;
+}
+
+// benchmarking override only (SURVEY.md §5 "config / flags"): FFTB200_SLAB_P2_CTAS = CTAs the exchange pass may use
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, int chunks) {
+    if (G < 1 || G > MAX_PEERS || rank < 0 || rank >= G) return FFTB200_INVALID_VALUE;
+    for (int d = 0; d < 3; ++d)
+        if (n[d] < 2 || !is_pow2(n[d])) return FFTB200_INVALID_SIZE;
+    if (!is_pow2(G) || n[0] % G || n[1] % G) return FFTB200_INVALID_SIZE;
+    std::unique_ptr<Plan> P(new Plan);
+    if (cudaGetDevice(&P->device) != cudaSuccess) { cudaGetLastError(); return FFTB200_SETUP_FAILED; }
+    P->type = type;
+    P->prec = (type == FFTB200_Z2Z || type == FFTB200_D2Z) ? 1 : 0;
+    P->real = (type == FFTB200_R2C || type == FFTB200_D2Z);
+    P->rank = 3;
+    P->batch = 1;
+    const int maxL = max_tile_length(P->prec);
+    if (n[0] > maxL || n[1] > maxL || (P->real ? n[2] / 2 : n[2]) > maxL || (P->real && n[2] < 4)) return FFTB200_INVALID_SIZE;
+    SlabState *S = new SlabState;
+    P->slab = S;
+    S->rank = rank;
+    S->G = G;
+    S->n0 = n[0]; S->n1 = n[1]; S->n2 = n[2];
+    S->n2c = P->real ? n[2] / 2 + 1 : n[2];
+    S->n0l = n[0] / G;
+    S->n1l = n[1] / G;
+    P->n[0] = S->n0l; P->n[1] = n[1]; P->n[2] = n[2];
+    const size_t ce = P->prec ? 16 : 8;
+    const long long vol = S->n0l * S->n1 * S->n2c;  // == n1l * n0 * n2c
+    Builder B;
+    B.P = P.get();
+    auto fail = [&](int code) {
+        free_plan_resources(P.get());
+        return code;
+    };
+    // chunking of the contiguous index (multiples of 16 columns keep every segment >= 128 B)
+    if (chunks < 1) chunks = 1;
+    long long cw = (S->n2c + chunks - 1) / chunks;
+    cw = (cw + 15) / 16 * 16;
+    S->J = (int)((S->n2c + cw - 1) / cw);
+    S->chunk_w = cw;
+    if (1 + S->J > 64) return fail(FFTB200_INVALID_VALUE);
+
+    if (cudaMalloc(&S->tmp, (size_t)vol * ce) != cudaSuccess) { cudaGetLastError(); return fail(FFTB200_ALLOC_FAILED); }
+    S->recv_bytes = (size_t)vol * ce;
+    S->flags_off = (S->recv_bytes + 255) / 256 * 256;
+    S->area_bytes = S->flags_off + sizeof(unsigned long long) * MAX_PEERS * 64;
+    if (cudaMalloc(&S->area, S->area_bytes) != cudaSuccess) { cudaGetLastError(); return fail(FFTB200_ALLOC_FAILED); }
+    if (cudaMemset((char *)S->area + S->flags_off, 0, S->area_bytes - S->flags_off) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
+    P->work_bytes = (size_t)vol * ce;
+
+    // ---- pass 1: x axis, in [n0l][n1][n2] -> tmp [n0l][n1][n2c]
+    {
+        std::vector<Level> lv;
+        if (P->real) {
+            lv.push_back({S->n0l * S->n1, S->n2 / 2, S->n2c});  // rows; input pitch in complex pairs
+            if (S->n2 & 1) return fail(FFTB200_INVALID_SIZE);
+            if (!add_tile_pass(B, V_RR_R2C, (int)(S->n2 / 2), 1, 1, lv, BUF_IN, BUF_WORK0, 0, "slab pass 1: x axis r2c"))
+                return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
+        } else {
+            lv.push_back({S->n0l * S->n1, S->n2, S->n2c});
+            if (!add_tile_pass(B, V_RR, (int)S->n2, 1, 1, lv, BUF_IN, BUF_WORK0, 0, "slab pass 1: x axis"))
+                return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
+        }
+        S->l_pass1 = (int)P->launches.size() - 1;
+    }
+    const int peer_shift = ilog2ll(S->n1l);
+    auto set_peer = [&](Launch &ln) {
+        ln.tp.peer_shift = peer_shift;
+        ln.tp.peer_mask = (int)S->n1l - 1;
+    };
+    // ---- pass 2, p2p: y axis on chunk j, tmp -> peers' recv [n1l][n0][n2c] at plane r*n0l + p
+    for (int j = 0; j < S->J; ++j) {
+        const long long c0 = j * cw, w = std::min(cw, S->n2c - c0);
+        std::vector<Level> lv = {{w, 1, 1}, {S->n0l, S->n1 * S->n2c, S->n2c}};
+        if (!add_tile_pass(B, V_CC_PEER, (int)S->n1, S->n2c, S->n0 * S->n2c, lv, BUF_WORK0, BUF_OUT, 0,
+                           "slab pass 2: y axis, store = exchange (peer memory)"))
+            return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
+        Launch &ln = P->launches.back();
+        ln.in_off = c0;
+        ln.out_off = (long long)rank * S->n0l * S->n2c + c0;
+        set_peer(ln);
+        // The exchange pass is NVLink-bound, not SM-bound: when it is pipelined against the z-axis pass
+        // keep it persistent on a bounded number of CTAs so that the HBM-bound pass finds free SMs.
+        if (G > 1 && S->J > 1) {
+            const unsigned cap = (unsigned)env_int("FFTB200_SLAB_P2_CTAS", 148);
+            if (cap > 0 && ln.grid > cap) ln.grid = std::max(1u, cap / ln.ki->cluster) * ln.ki->cluster;
+        }
+        S->l_pass2.push_back((int)P->launches.size() - 1);
+    }
+    // ---- pass 3, p2p: z axis on chunk j, recv [n1l][n0][n2c] -> out (same layout)
+    for (int j = 0; j < S->J; ++j) {
+        const long long c0 = j * cw, w = std::min(cw, S->n2c - c0);
+        std::vector<Level> lv = {{w, 1, 1}, {S->n1l, S->n0 * S->n2c, S->n0 * S->n2c}};
+        if (!add_tile_pass(B, V_CC, (int)S->n0, S->n2c, S->n2c, lv, BUF_WORK1, BUF_OUT, 0, "slab pass 3: z axis"))
+            return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
+        Launch &ln = P->launches.back();
+        ln.in_off = c0;
+        ln.out_off = c0;
+        S->l_pass3.push_back((int)P->launches.size() - 1);
+    }
+    // ---- staged mode: pass 2 into the G blocks [d][n0l][n1l][n2c] of a send buffer ...
+    {
+        std::vector<Level> lv = {{S->n2c, 1, 1}, {S->n0l, S->n1 * S->n2c, S->n1l * S->n2c}};
+        if (!add_tile_pass(B, V_CC_PEER, (int)S->n1, S->n2c, S->n2c, lv, BUF_WORK0, BUF_OUT, 0,
+                           "slab pass 2 (staged): y axis, store = pack into all-to-all blocks"))
+            return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
+        set_peer(P->launches.back());
+        S->l_pre2 = (int)P->launches.size() - 1;
+    }
+    // ... and pass 3 from the received blocks [s][n0l][n1l][n2c] == [n0][n1l][n2c] -> out [n1l][n0][n2c]
+    {
+        std::vector<Level> lv = {{S->n2c, 1, 1}, {S->n1l, S->n2c, S->n0 * S->n2c}};
+        if (!add_tile_pass(B, V_CC, (int)S->n0, S->n1l * S->n2c, S->n2c, lv, BUF_IN, BUF_OUT, 0,
+                           "slab pass 3 (staged): z axis, load = unpack"))
+            return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
+        S->l_post3 = (int)P->launches.size() - 1;
+    }
+    if (cudaStreamCreateWithFlags(&S->aux, cudaStreamNonBlocking) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
+    S->ev_chunk.assign(S->J, nullptr);
+    for (int j = 0; j < S->J; ++j)
+        if (cudaEventCreateWithFlags(&S->ev_chunk[j], cudaEventDisableTiming) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
+    if (cudaEventCreateWithFlags(&S->ev_done, cudaEventDisableTiming) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
+    for (int i = 0; i < 5; ++i)
+        if (cudaEventCreate(&S->ev_t[i]) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
+    S->peer_area[rank] = S->area;
+    if (G == 1) S->connected = true;
+    *out = P.release();
+    return FFTB200_SUCCESS;
+}
+
+static unsigned long long *slab_flags(SlabState *S, int d) {
+    return (unsigned long long *)((char *)S->peer_area[d] + S->flags_off);
+}
+
+// fused exchange: every rank calls this once per transform (collective)
+static int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
+    SlabState *S = P->slab;
+    if (!S->connected) return FFTB200_INVALID_PLAN;
+    DeviceGuard g(P->device);
+    std::lock_guard<std::mutex> lk(P->mu);
+    cudaStream_t st = P->stream;
+    const unsigned long long epoch = ++S->epoch;
+    SlabPeers peers;
+    void *recv[MAX_PEERS];
+    for (int d = 0; d < MAX_PEERS; ++d) {
+        peers.flags[d] = d < S->G ? slab_flags(S, d) : nullptr;
+        recv[d] = d < S->G ? S->peer_area[d] : nullptr;
+    }
+    if (S->timing) cudaEventRecord(S->ev_t[0], st);
+    // my receive buffer is free again (stream order: after my previous transform's pass 3)
+    if (S->G > 1) slab_signal_kernel<<<1, 32, 0, st>>>(peers, S->G, S->rank, 0, epoch);
+    int rc = slab_launch(P, S->l_pass1, in, S->tmp, nullptr, inverse, st);
+    if (rc) return rc;
+    if (S->timing) cudaEventRecord(S->ev_t[1], st);
+    if (S->G > 1) slab_wait_kernel<<<1, 32, 0, st>>>(slab_flags(S, S->rank), S->G, 0, epoch);
+    for (int j = 0; j < S->J; ++j) {
+        rc = slab_launch(P, S->l_pass2[j], S->tmp, nullptr, recv, inverse, st);
+        if (rc) return rc;
+        if (S->G > 1) slab_signal_kernel<<<1, 32, 0, st>>>(peers, S->G, S->rank, 1 + j, epoch);
+        if (j == S->J - 1 && S->timing) cudaEventRecord(S->ev_t[2], st);
+        cudaStream_t s3 = (S->J > 1) ? S->aux : st;
+        if (S->J > 1) {
+            cudaEventRecord(S->ev_chunk[j], st);
+            cudaStreamWaitEvent(s3, S->ev_chunk[j], 0);
+        }
+        if (S->G > 1) slab_wait_kernel<<<1, 32, 0, s3>>>(slab_flags(S, S->rank), S->G, 1 + j, epoch);
+        rc = slab_launch(P, S->l_pass3[j], S->area, out, nullptr, inverse, s3);
+        if (rc) return rc;
+    }
+    if (S->J > 1) {
+        cudaEventRecord(S->ev_done, S->aux);
+        cudaStreamWaitEvent(st, S->ev_done, 0);
+    }
+    if (S->timing) cudaEventRecord(S->ev_t[3], st);
+    return cudaGetLastError() == cudaSuccess ? FFTB200_SUCCESS : FFTB200_EXEC_FAILED;
+}
+
+static int slab_exec_pre(Plan *P, const void *in, void *send, int inverse) {
+    SlabState *S = P->slab;
+    DeviceGuard g(P->device);
+    std::lock_guard<std::mutex> lk(P->mu);
+    const size_t ce = P->prec ? 16 : 8;
+    int rc = slab_launch(P, S->l_pass1, in, S->tmp, nullptr, inverse, P->stream);
+    if (rc) return rc;
+    void *blocks[MAX_PEERS] = {};
+    for (int d = 0; d < S->G; ++d) blocks[d] = (char *)send + (size_t)d * S->n0l * S->n1l * S->n2c * ce;
+    return slab_launch(P, S->l_pre2, S->tmp, nullptr, blocks, inverse, P->stream);
+}
+
+static int slab_exec_post(Plan *P, const void *recv, void *out, int inverse) {
+    SlabState *S = P->slab;
+    DeviceGuard g(P->device);
+    std::lock_guard<std::mutex> lk(P->mu);
+    return slab_launch(P, S->l_post3, recv, out, nullptr, inverse, P->stream);
+}

@@ -25,6 +25,8 @@
 // dft/dftw-direct.c:46-56 twiddle codelets, dft/rank-geq2.c:42-52 axis split,
 // rdft/ct-hc2c.c:59-70 r2c post-pass) — here one fused kernel per axis.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "butterfly.cuh"
 
 namespace fftb200 {
@@ -52,6 +54,7 @@ struct TileParams {
     const double2 *tw4_lo;
     long long in_ls, in_is, in_os1, in_os2;
     long long out_ls, out_is, out_os1, out_os2;
+    int n_tiles;   // tiles of the whole pass (a CTA loops over tile = blockIdx.x + k * gridDim.x)
     int n_inner;   // lines along the inner index
     int n_o2;      // outer index o = o1*n_o2 + o2
     int tiles_per_outer;
@@ -77,68 +80,45 @@ template <typename T, int L_, int R_, int W_, int VAR_> struct TileTraits {
     static constexpr bool STORE_ROW = (VAR == V_RR || VAR == V_RR_R2C);
     static constexpr bool NEED_SMEM = (S > 1) || (VAR == V_RR_R2C);
     static constexpr int SMEM_BYTES = NEED_SMEM ? L * W * (int)sizeof(cplx<T>) : 0;
-    // swizzle group width: 8 x 16 B or 16 x 8 B = 128 B = all 32 banks
-    static constexpr int SWZ_BITS = sizeof(cplx<T>) == 16 ? 3 : 4;
+    // swizzle group width: 8 x 16 B or 16 x 8 B = 128 B = all 32 banks.  Pure column passes need no
+    // swizzle at all: their lanes run along w first, so every quarter-warp (16-byte elements) or
+    // half-warp (8-byte elements) touches one contiguous, aligned 128-byte run whatever the row; the
+    // index arithmetic then folds into immediate offsets.
+    static constexpr bool SWIZZLED = LOAD_ROW || STORE_ROW || (W * (int)sizeof(cplx<T>) < 128);
+    static constexpr int SWZ_BITS = !SWIZZLED ? 0 : (sizeof(cplx<T>) == 16 ? 3 : 4);
     static_assert(R * T_LINE == L, "R must divide L");
     static_assert(S == 1 || R_LAST <= R, "bad stage split");
 };
 
 // XOR-fold of x's bits above the low group, in groups of BITS
 template <int BITS, int TOTAL_BITS> __device__ __forceinline__ int swz_fold(int idx) {
-    int f = 0;
+    if constexpr (BITS == 0) {
+        return 0;
+    } else {
+        int f = 0;
 #pragma unroll
-    for (int s = BITS; s < TOTAL_BITS; s += BITS) f ^= (idx >> s);
-    return f & ((1 << BITS) - 1);
+        for (int s = BITS; s < TOTAL_BITS; s += BITS) f ^= (idx >> s);
+        return f & ((1 << BITS) - 1);
+    }
 }
 
 template <typename T> __device__ __forceinline__ cplx<T> ld_cplx(const cplx<T> *p) { return __ldg(p); }
 
+// ---------------------------------------------------------------------------------------------
+// All radix stages of one tile.  In: thread (w1, u1) holds x[u1 + d*T_LINE], d < R, of line w1 in v[].
+// Out: thread (wl, ul) holds X[k], k = (ul + b*T_LINE) + q*(L/RL), in v[b*RL + q]  (B*RL == R).
+// (w1,u1) follows the load style, (wl,ul) the store style.
+// ---------------------------------------------------------------------------------------------
 template <typename T, int L, int R, int W, int VAR>
-__global__ void __launch_bounds__(TileTraits<T, L, R, W, VAR>::THREADS)
-fft_tile_kernel(const TileParams p) {
+__device__ __forceinline__ void tile_stages(cplx<T> *v, cplx<T> *sm, const cplx<T> *__restrict__ tw, const int w1,
+                                            const int u1, const int w_col, const int u_col, const int wl, const int ul) {
     using TR = TileTraits<T, L, R, W, VAR>;
-    using C = cplx<T>;
     constexpr int S = TR::S;
     constexpr int LOG_R = TR::LOG_R, LOG_W = TR::LOG_W, LOG_L = TR::LOG_L;
-    constexpr int T_LINE = TR::T_LINE, LOG_TL = TR::LOG_TL;
+    constexpr int T_LINE = TR::T_LINE;
     constexpr int R_LAST = TR::R_LAST;
     constexpr int IDX_BITS = LOG_L + LOG_W;
     constexpr int SB = TR::SWZ_BITS;
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C *sm = reinterpret_cast<C *>(smem_raw);
-
-    const int t = threadIdx.x;
-    // thread -> (line w within tile, slot u within line), for the two access styles
-    const int w_col = t & (W - 1), u_col = t >> LOG_W;
-    const int u_row = t & (T_LINE - 1), w_row = t >> LOG_TL;
-
-    const int tile = blockIdx.x;
-    const int o = tile / p.tiles_per_outer;
-    const int i0 = (tile - o * p.tiles_per_outer) * W;
-    const int o1 = o / p.n_o2, o2 = o - o1 * p.n_o2;
-    const C *__restrict__ gin = reinterpret_cast<const C *>(p.in) + o1 * p.in_os1 + o2 * p.in_os2;
-    C *__restrict__ gout = reinterpret_cast<C *>(p.out) + o1 * p.out_os1 + o2 * p.out_os2;
-    const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);
-    const bool inv = p.inverse != 0;
-
-    C v[R];
-
-    // ------------------------------------------------------------------ stage 1: HBM -> registers
-    const int w1 = TR::LOAD_ROW ? w_row : w_col;
-    const int u1 = TR::LOAD_ROW ? u_row : u_col;
-    {
-        const bool ok = (i0 + w1) < p.n_inner;
-        const C *src = gin + (long long)(i0 + w1) * p.in_is + (long long)u1 * p.in_ls;
-#pragma unroll
-        for (int d = 0; d < R; ++d) {
-            C x = mk<T>((T)0, (T)0);
-            if (ok) x = ld_cplx<T>(src + (long long)(d * T_LINE) * p.in_ls);
-            if (inv) { T s = x.x; x.x = x.y; x.y = s; }
-            v[d] = x;
-        }
-    }
-
     if constexpr (S > 1) {
         fft_reg<T, R>(v);
         // twiddle w_L^(d*u1), then park at position d*m_1 + u1
@@ -188,8 +168,6 @@ fft_tile_kernel(const TileParams p) {
         // -------------------------------------------------------------- last stage: smem -> registers
         {
             constexpr int B = R / R_LAST;  // butterflies per thread
-            const int wl = TR::STORE_ROW ? w_row : w_col;
-            const int ul = TR::STORE_ROW ? u_row : u_col;
 #pragma unroll
             for (int b = 0; b < B; ++b) {
                 const int jp = ul + b * T_LINE;  // output-order index of this butterfly, in [0, L/R_LAST)
@@ -213,13 +191,103 @@ fft_tile_kernel(const TileParams p) {
     } else {
         fft_reg<T, R>(v);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Store of one tile's results (all variants but r2c).  The line's global output index of local index k
+// is KADD + KMUL*k (KMUL = KADD = trivial for single-CTA tiles; a cluster CTA owns the residue class
+// k1 = KADD of a length KMUL*L line).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int L, int R, int W, int VAR>
+__device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p, const int o1, const int o2, const int i0,
+                                           const int wl, const int ul, const int kmul, const int kadd) {
+    using TR = TileTraits<T, L, R, W, VAR>;
+    using C = cplx<T>;
+    constexpr int S = TR::S;
+    constexpr int T_LINE = TR::T_LINE;
+    constexpr int B = (S > 1) ? R / TR::R_LAST : 1;
+    constexpr int RL = (S > 1) ? TR::R_LAST : R;
+    const bool inv = p.inverse != 0;
+    const bool ok = (i0 + wl) < p.n_inner;
+    const long long off = o1 * p.out_os1 + o2 * p.out_os2 + (long long)(i0 + wl) * p.out_is;
+    C *dst = reinterpret_cast<C *>(p.out) + off;
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+#pragma unroll
+        for (int q = 0; q < RL; ++q) {
+            const int k = kadd + kmul * ((ul + b * T_LINE) + q * (L / RL));
+            C x = v[b * RL + q];
+            if constexpr (VAR == V_CC_TW) {
+                // four-step twiddle w_N^(i*k), N = L * n_inner; two-level fp64 table
+                const long long m = (long long)(i0 + wl) * k;
+                const double2 wh = __ldg(p.tw4_hi + (m >> p.tw4_shift));
+                const double2 wlw = __ldg(p.tw4_lo + (m & p.tw4_mask));
+                const double wr = wh.x * wlw.x - wh.y * wlw.y;
+                const double wi = wh.x * wlw.y + wh.y * wlw.x;
+                const double xr = (double)x.x * wr - (double)x.y * wi;
+                const double xi = (double)x.x * wi + (double)x.y * wr;
+                x.x = (T)xr; x.y = (T)xi;
+            }
+            if (inv) { T s = x.x; x.x = x.y; x.y = s; }
+            if constexpr (VAR == V_CC_PEER) {
+                C *pd = reinterpret_cast<C *>(p.peer[k >> p.peer_shift]) + off;
+                if (ok) pd[(long long)(k & p.peer_mask) * p.out_ls] = x;
+            } else {
+                if (ok) dst[(long long)k * p.out_ls] = x;
+            }
+        }
+}
+
+template <typename T, int L, int R, int W, int VAR>
+__device__ __forceinline__ void fft_tile_body(const TileParams &p, const int tile, unsigned char *smem_raw) {
+    using TR = TileTraits<T, L, R, W, VAR>;
+    using C = cplx<T>;
+    constexpr int S = TR::S;
+    constexpr int LOG_W = TR::LOG_W, LOG_L = TR::LOG_L;
+    constexpr int T_LINE = TR::T_LINE, LOG_TL = TR::LOG_TL;
+    constexpr int IDX_BITS = LOG_L + LOG_W;
+    constexpr int SB = TR::SWZ_BITS;
+
+    C *sm = reinterpret_cast<C *>(smem_raw);
+
+    const int t = threadIdx.x;
+    // thread -> (line w within tile, slot u within line), for the two access styles
+    const int w_col = t & (W - 1), u_col = t >> LOG_W;
+    const int u_row = t & (T_LINE - 1), w_row = t >> LOG_TL;
+
+    const int o = tile / p.tiles_per_outer;
+    const int i0 = (tile - o * p.tiles_per_outer) * W;
+    const int o1 = o / p.n_o2, o2 = o - o1 * p.n_o2;
+    const C *__restrict__ gin = reinterpret_cast<const C *>(p.in) + o1 * p.in_os1 + o2 * p.in_os2;
+    C *__restrict__ gout = reinterpret_cast<C *>(p.out) + o1 * p.out_os1 + o2 * p.out_os2;
+    const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);
+    const bool inv = p.inverse != 0;
+
+    C v[R];
+
+    // ------------------------------------------------------------------ stage 1: HBM -> registers
+    const int w1 = TR::LOAD_ROW ? w_row : w_col;
+    const int u1 = TR::LOAD_ROW ? u_row : u_col;
+    {
+        const bool ok = (i0 + w1) < p.n_inner;
+        const C *src = gin + (long long)(i0 + w1) * p.in_is + (long long)u1 * p.in_ls;
+#pragma unroll
+        for (int d = 0; d < R; ++d) {
+            C x = mk<T>((T)0, (T)0);
+            if (ok) x = ld_cplx<T>(src + (long long)(d * T_LINE) * p.in_ls);
+            if (inv) { T s = x.x; x.x = x.y; x.y = s; }
+            v[d] = x;
+        }
+    }
+
+    const int wl = TR::STORE_ROW ? w_row : w_col;
+    const int ul = TR::STORE_ROW ? u_row : u_col;
+    tile_stages<T, L, R, W, VAR>(v, sm, tw, w1, u1, w_col, u_col, wl, ul);
 
     // After the last stage thread (wl, ul) holds, for b in [0,B) and q in [0,R_LAST):
     //   X[k],  k = (ul + b*T_LINE) + q*(L/R_LAST),  in v[b*R_LAST + q]
-    constexpr int B = (S > 1) ? R / R_LAST : 1;
-    constexpr int RL = (S > 1) ? R_LAST : R;
-    const int wl = TR::STORE_ROW ? w_row : w_col;
-    const int ul = TR::STORE_ROW ? u_row : u_col;
+    constexpr int B = (S > 1) ? R / TR::R_LAST : 1;
+    constexpr int RL = (S > 1) ? TR::R_LAST : R;
 
     if constexpr (VAR == V_RR_R2C) {
         // ---- even/odd post-pass (cf. rdft/ct-hc2c.c:59-70): the line held L complex = 2L reals.
@@ -257,37 +325,140 @@ fft_tile_kernel(const TileParams p) {
                 dst[(long long)(L - k) * p.out_ls] = cconj(csub(e, wo));
             }
         }
-        return;
     } else {
-        const bool ok = (i0 + wl) < p.n_inner;
-        C *dst = gout + (long long)(i0 + wl) * p.out_is;
+        tile_store<T, L, R, W, VAR>(v, p, o1, o2, i0, wl, ul, 1, 0);
+    }
+}
+
+// The kernel: CTA b transforms tiles b, b + gridDim.x, ...  With gridDim.x == n_tiles (the default) every
+// CTA owns one tile; a smaller grid makes the pass persistent on a bounded number of SMs, which is how
+// the slab plans keep an NVLink-bound exchange pass and an HBM-bound local pass running side by side.
+template <typename T, int L, int R, int W, int VAR>
+__global__ void __launch_bounds__(TileTraits<T, L, R, W, VAR>::THREADS)
+fft_tile_kernel(const TileParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        fft_tile_body<T, L, R, W, VAR>(p, tile, smem_raw);
+        if (TileTraits<T, L, R, W, VAR>::NEED_SMEM && tile + (int)gridDim.x < p.n_tiles) __syncthreads();
+    }
+}
+
+// distributed shared memory through 32-bit shared::cluster addresses (cheaper in registers than
+// generic pointers from cluster.map_shared_rank)
+__device__ __forceinline__ unsigned dsmem_map(unsigned local_addr, unsigned cta_rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ double2 dsmem_ld(unsigned addr, double2 *) {
+    double2 v;
+    asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 dsmem_ld(unsigned addr, float2 *) {
+    float2 v;
+    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dsmem_st(unsigned addr, double2 v) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void dsmem_st(unsigned addr, float2 v) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cluster pass for long strided axes: a thread-block cluster of CL CTAs transforms W lines of length
+// L = CL*LL, so that a tile keeps 128-byte HBM segments (W*sizeof(complex) = 128 B) although L*W
+// complex do not fit one SM.  CTA c of the cluster
+//   A. loads, for its share of the positions j (LL/CL of them), the CL rows d*LL + j straight from HBM
+//      (each still a 128-byte segment), does the CL-point DFT over d in registers, multiplies by
+//      w_L^(j*k1) and scatters y_k1[j] into CTA k1's shared memory (distributed shared memory stores),
+//   B. after one cluster barrier transforms the length-LL sub-sequence it now owns (k1 = c) with the
+//      ordinary stage pipeline and stores X[c + CL*k'], k' < LL.
+// (decimation in frequency: X[k1 + CL*k'] = DFT_LL( DFT_CL_d(x[d*LL+j])(k1) * w_L^(j*k1) )[k'])
+// ---------------------------------------------------------------------------------------------
+template <typename T, int LL, int CL, int R, int W, int VAR>
+__global__ void __launch_bounds__(TileTraits<T, LL, R, W, VAR>::THREADS,
+                                  (TileTraits<T, LL, R, W, VAR>::SMEM_BYTES <= 100 * 1024 &&
+                                   TileTraits<T, LL, R, W, VAR>::THREADS * 2 <= 1024 && sizeof(T) * R <= 64) ? 2 : 1)
+fft_cluster_kernel(const TileParams p) {
+    namespace cg = cooperative_groups;
+    using TR = TileTraits<T, LL, R, W, VAR>;
+    using C = cplx<T>;
+    static_assert(!TR::LOAD_ROW && !TR::STORE_ROW, "cluster passes are column passes");
+    static_assert(R % CL == 0 && TR::S > 1, "cross stage needs R/CL items per thread");
+    constexpr int LOG_W = TR::LOG_W, LOG_L = TR::LOG_L;
+    constexpr int T_LINE = TR::T_LINE;
+    constexpr int IDX_BITS = LOG_L + LOG_W;
+    constexpr int SB = TR::SWZ_BITS;
+    constexpr int NI = R / CL;  // cross-stage items per thread
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *sm = reinterpret_cast<C *>(smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
+    const int n_clusters = (int)gridDim.x / CL;
+    const unsigned sm_base = (unsigned)__cvta_generic_to_shared(sm);
+
+    const int t = threadIdx.x;
+    const int w = t & (W - 1), u = t >> LOG_W;
+    const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);       // w_LL^k
+    const C *__restrict__ twL = reinterpret_cast<const C *>(p.tw_aux);  // w_L^k
+    const bool inv = p.inverse != 0;
+
+    // every CTA of the cluster must be running before its shared memory is written remotely: arrive now,
+    // wait just before the first scatter (the HBM loads in between hide the barrier)
+    cluster.barrier_arrive();
+    bool first = true;
+    for (int tile = (int)blockIdx.x / CL; tile < p.n_tiles; tile += n_clusters) {
+        const int o = tile / p.tiles_per_outer;
+        const int i0 = (tile - o * p.tiles_per_outer) * W;
+        const int o1 = o / p.n_o2, o2 = o - o1 * p.n_o2;
+        const C *__restrict__ gin = reinterpret_cast<const C *>(p.in) + o1 * p.in_os1 + o2 * p.in_os2;
+        C v[R];
+        // ---- A: HBM -> registers -> cross-CTA radix-CL stage -> owners' shared memory
+        {
+            const bool ok = (i0 + w) < p.n_inner;
+            const int j0 = c * (LL / CL) + u;
+            const C *src = gin + (long long)(i0 + w) * p.in_is + (long long)j0 * p.in_ls;
 #pragma unroll
-        for (int b = 0; b < B; ++b)
+            for (int it = 0; it < NI; ++it)
 #pragma unroll
-            for (int q = 0; q < RL; ++q) {
-                const int k = (ul + b * T_LINE) + q * (L / RL);
-                C x = v[b * RL + q];
-                if constexpr (VAR == V_CC_TW) {
-                    // four-step twiddle w_N^(i*k), N = L * n_inner; two-level fp64 table
-                    const long long m = (long long)(i0 + wl) * k;
-                    const double2 wh = __ldg(p.tw4_hi + (m >> p.tw4_shift));
-                    const double2 wlw = __ldg(p.tw4_lo + (m & p.tw4_mask));
-                    const double wr = wh.x * wlw.x - wh.y * wlw.y;
-                    const double wi = wh.x * wlw.y + wh.y * wlw.x;
-                    const double xr = (double)x.x * wr - (double)x.y * wi;
-                    const double xi = (double)x.x * wi + (double)x.y * wr;
-                    x.x = (T)xr; x.y = (T)xi;
+                for (int d = 0; d < CL; ++d) {
+                    C x = mk<T>((T)0, (T)0);
+                    if (ok) x = ld_cplx<T>(src + (long long)(d * LL + it * T_LINE) * p.in_ls);
+                    if (inv) { T s = x.x; x.x = x.y; x.y = s; }
+                    v[it * CL + d] = x;
                 }
-                if (inv) { T s = x.x; x.x = x.y; x.y = s; }
-                if constexpr (VAR == V_CC_PEER) {
-                    C *pd = reinterpret_cast<C *>(p.peer[k >> p.peer_shift]) + o1 * p.out_os1 + o2 * p.out_os2 +
-                            (long long)(i0 + wl) * p.out_is;
-                    if (ok) pd[(long long)(k & p.peer_mask) * p.out_ls] = x;
-                } else {
-                    if (ok) dst[(long long)k * p.out_ls] = x;
+            if (first) { cluster.barrier_wait(); first = false; }
+#pragma unroll
+            for (int it = 0; it < NI; ++it) {
+                const int j = j0 + it * T_LINE;
+                const int idx = (j << LOG_W) | w;
+                const unsigned sa = sm_base + (unsigned)(idx ^ swz_fold<SB, IDX_BITS>(idx)) * (unsigned)sizeof(C);
+                fft_reg<T, CL>(v + it * CL);
+#pragma unroll
+                for (int k1 = 0; k1 < CL; ++k1) {
+                    C y = v[it * CL + k1];
+                    if (k1 > 0) y = cmul(y, ld_cplx<T>(twL + j * k1));
+                    dsmem_st(dsmem_map(sa, k1), y);
                 }
             }
+        }
+        cluster.sync();
+        // ---- B: local length-LL transform of sub-sequence k1 = c, then store rows c + CL*k'
+#pragma unroll
+        for (int d = 0; d < R; ++d) {
+            const int idx = ((u + d * T_LINE) << LOG_W) | w;
+            v[d] = sm[idx ^ swz_fold<SB, IDX_BITS>(idx)];
+        }
+        tile_stages<T, LL, R, W, VAR>(v, sm, tw, w, u, w, u, w, u);
+        tile_store<T, LL, R, W, VAR>(v, p, o1, o2, i0, w, u, CL, c);
+        // persistent launch: nobody may scatter the next tile into a CTA that still works on this one
+        if (tile + n_clusters < p.n_tiles) cluster.sync();
     }
+    if (first) cluster.barrier_wait();
 }
 
 }  // namespace fftb200

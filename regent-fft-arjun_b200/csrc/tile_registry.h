@@ -7,6 +7,7 @@ namespace fftb200 {
 struct TileKernelInfo {
     void (*fn)(const TileParams);
     int L, R, W, threads, smem_bytes;
+    int cluster;  // CTAs per thread-block cluster (1 = ordinary launch); L = cluster * (length one CTA holds)
 };
 
 // prec: 0 = fp32 (complex32), 1 = fp64 (complex64).  Returns nullptr when L is not compiled.

@@ -201,7 +201,8 @@ def test_every_power_of_two_axis_kernel(L, oracle, kind):
 
 
 SHAPES = [((64, 64), 1), ((32, 256), 2), ((256, 32), 1), ((16, 8, 32), 1), ((64, 64, 64), 1), ((128, 4, 512), 1),
-          ((8, 1024, 4), 1), ((1, 64, 1), 1), ((2, 2), 1), ((4, 4, 4), 5),
+          ((8, 1024, 4), 1), ((1, 64, 1), 1), ((4096, 64), 1), ((2048, 32), 2), ((1024, 16, 8), 1), ((8192, 16), 1),
+          ((2, 2048, 24), 1), ((2, 2), 1), ((4, 4, 4), 5),
           ((3,), 1), ((5,), 2), ((12,), 1), ((1021,), 1), ((3, 2, 2), 1), ((6, 10, 9), 2), ((7, 16), 1), ((1,), 1),
           ((1 << 15,), 1), ((1 << 18,), 2), ((1 << 20,), 1), ((1 << 22,), 1)]
 
@@ -217,6 +218,23 @@ def test_shapes_against_oracle(L, oracle, kind):
         got, _ = gpu_fft(L, kind, x, shape, batch)
         err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape, batch))
         assert err <= oracle.tolerance(int(np.prod(shape)), kind in ("c2c", "r2c")), (kind, shape, batch, err)
+
+
+def test_long_strided_axes_use_cluster_kernels(L, oracle):
+    """strided axes of 1024..16384 points run as thread-block-cluster passes (DSMEM cross stage)"""
+    for kind, shape in [("z2z", (1024, 64)), ("z2z", (2048, 8)), ("z2z", (4096, 16)), ("z2z", (8192, 8)),
+                        ("c2c", (1024, 32)), ("c2c", (2048, 16)), ("c2c", (4096, 48 // 3)), ("c2c", (8192, 16)),
+                        ("c2c", (16384, 8)), ("d2z", (4096, 64)), ("r2c", (2048, 128))]:
+        _, dt_in, _ = _kinds(L)[kind]
+        x = oracle.synth(shape, dt_in, 600 + shape[0] % 97)
+        got, desc = gpu_fft(L, kind, x, shape)
+        err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape))
+        assert err <= oracle.tolerance(int(np.prod(shape)), kind in ("c2c", "r2c")), (kind, shape, err)
+        assert "cluster=%d" % {1024: 2, 2048: 4, 4096: 8, 8192: 8, 16384: 8}[shape[0]] in desc, desc
+        # backward transform through the same kernels
+        if kind in ("z2z", "c2c"):
+            back, _ = gpu_fft(L, kind, got, shape, direction=+1)
+            assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * oracle.tolerance(int(np.prod(shape)), kind == "c2c")
 
 
 def test_baseline_config1_n1024(L, oracle):
@@ -512,7 +530,10 @@ def test_native_library_is_the_one_running(fft, L):
     """the product path is libfft_b200.so in-tree; the launch list shows hand-written kernels"""
     assert os.path.samefile(L.LIB_PATH, os.path.join(os.path.dirname(fft.__file__), "libfft_b200.so"))
     maps = open("/proc/self/maps").read()
-    assert "libfft_b200.so" in maps and "libcufft" not in maps
+    assert "libfft_b200.so" in maps
+    import subprocess
+    needed = subprocess.run(["readelf", "-d", L.LIB_PATH], capture_output=True, text=True).stdout
+    assert "NEEDED" in needed and "cufft" not in needed.lower() and "nccl" not in needed.lower(), needed
     h = L.plan_many(3, [512, 512, 512], None, 0, 0, None, 0, 0, L.Z2Z, 1)
     assert L.launch_count(h) == 3 and L.work_size(h) == 0
     total = sum(L.launch_bytes(h, i) for i in range(3))

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu5.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu5.log
+tail -15 gpurun_out/pytest_gpu5.log
+python tools/cufft_compare.py 2>&1 | tee gpurun_out/cufft_compare2.log
+for n in 512 1024; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29556 tools/slab_probe.py $n z2z 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tee -a gpurun_out/slab_probe3_n2.log
+done
