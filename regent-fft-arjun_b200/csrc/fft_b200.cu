@@ -42,9 +42,16 @@ static table_fn k_tables[2][V_COUNT] = {
 const TileKernelInfo *find_tile_kernel(int prec, int variant, int L) {
     int n = 0;
     const TileKernelInfo *t = k_tables[prec][variant](&n);
+    // FFTB200_TILE_ALT=k (tuning experiments only): take the k-th alternative row compiled for this length
+    const char *alt = getenv("FFTB200_TILE_ALT");
+    int skip = (alt && *alt) ? atoi(alt) : 0;
+    const TileKernelInfo *first = nullptr;
     for (int i = 0; i < n; ++i)
-        if (t[i].L == L) return &t[i];
-    return nullptr;
+        if (t[i].L == L) {
+            if (!first) first = &t[i];
+            if (skip-- == 0) return &t[i];
+        }
+    return first;
 }
 
 int max_tile_length(int prec) {
@@ -102,10 +109,16 @@ static cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStre
 enum BufSel { BUF_IN = 0, BUF_OUT = 1, BUF_WORK0 = 2, BUF_WORK1 = 3 };
 
 struct Launch {
-    enum Kind { TILE, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER } kind = TILE;
+    enum Kind { TILE, FUSED, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER } kind = TILE;
     // TILE
     const TileKernelInfo *ki = nullptr;
     TileParams tp{};
+    int variant = 0;
+    // FUSED (two axis passes in one persistent kernel; tp = pass A, tp_b = pass B)
+    const FusedKernelInfo *fk = nullptr;
+    TileParams tp_b{};
+    unsigned *counters = nullptr;
+    int tiles_a = 0, tiles_b = 0, n_groups = 0, lag = 0;
     // generic
     GenLayout lay{};
     long long total = 0, outer = 0, inner = 0;
@@ -315,6 +328,7 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     Launch ln;
     ln.kind = Launch::TILE;
     ln.ki = ki;
+    ln.variant = variant;
     ln.src = src;
     ln.dst = dst;
     TileParams &tp = ln.tp;
@@ -389,6 +403,82 @@ static std::vector<int> split_1d(long long N, int prec) {
     }
     (void)prec;
     return f;
+}
+
+// Fuse the contiguous-axis pass and the following strided-axis pass into one persistent kernel when both
+// use the same CTA shape and the first pass's tiles enumerate whole planes in order (dense layouts).
+// FFTB200_NO_FUSE=1 keeps the separate passes (benchmarking only).
+static int env_int_or(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+static void try_fuse_first_two(Builder &B) {
+    Plan *P = B.P;
+    if (P->real || P->launches.size() < 2) return;
+    // Opt-in (FFTB200_FUSE=1).  Measured on B200 at 512^3 fp64: the fused kernel cuts HBM traffic of the two
+    // passes from 8.5 GB to 4.25 GB (ncu dram__bytes), but both forms are bound by per-tile latency at two
+    // CTAs per SM, not by HBM, and the ticket/flag traffic makes the fused form ~5 % slower (1.59 vs 1.51 ms).
+    const char *fu = getenv("FFTB200_FUSE");
+    if (!(fu && *fu && *fu != '0')) return;
+    Launch &a = P->launches[0], &b = P->launches[1];
+    if (a.kind != Launch::TILE || b.kind != Launch::TILE || a.variant != V_RR || b.variant != V_CC) return;
+    if (a.ki->cluster != 1 || b.ki->cluster != 1 || a.dst != BUF_OUT || b.src != BUF_OUT || b.dst != BUF_OUT) return;
+    const FusedKernelInfo *fk = find_fused_kernel(P->prec, a.ki->L, b.ki->L);
+    if (!fk) return;
+    if (a.ki->R != fk->RA || a.ki->W != fk->WA || b.ki->R != fk->RB || b.ki->W != fk->WB) return;
+    if (a.tp.n_tiles != a.tp.tiles_per_outer) return;  // pass A must be one dense run of rows
+    const long long planes = b.tp.n_tiles / b.tp.tiles_per_outer;
+    if (planes < 8 || a.tp.n_tiles % planes) return;
+    const long long ta_plane = a.tp.n_tiles / planes, tb_plane = b.tp.tiles_per_outer;
+    // rows of pass A per plane must equal the line length of pass B
+    if (ta_plane * a.ki->W != b.ki->L) return;
+    const long long want_tiles = env_int_or("FFTB200_FUSE_TILES", 128);  // benchmarking override
+    long long Pg = (want_tiles + ta_plane - 1) / ta_plane;
+    if (Pg < 1) Pg = 1;
+    while (Pg < planes && planes % Pg) ++Pg;
+    if (planes % Pg) return;
+    const long long n_groups = planes / Pg;
+    const int lag = env_int_or("FFTB200_FUSE_LAG", 2);
+    if (lag < 1 || n_groups < 2 * lag) return;
+    unsigned *counters = (unsigned *)B.alloc(sizeof(unsigned) * (size_t)(1 + n_groups));
+    if (!counters) return;
+    int sms = 148, per_sm = fk->min_ctas;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P->device);
+    if (fk->smem_bytes > 48 * 1024 &&
+        cudaFuncSetAttribute((const void *)fk->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fk->smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fk->fn, fk->threads, fk->smem_bytes) != cudaSuccess ||
+        per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    Launch f = a;
+    f.kind = Launch::FUSED;
+    f.fk = fk;
+    f.tp_b = b.tp;
+    f.counters = counters;
+    f.tiles_a = (int)(ta_plane * Pg);
+    f.tiles_b = (int)(tb_plane * Pg);
+    f.n_groups = (int)n_groups;
+    f.lag = lag;
+    const long long total = (long long)(f.tiles_a + f.tiles_b) * n_groups;
+    f.grid = (unsigned)std::min<long long>(total, (long long)sms * per_sm);
+    f.src = a.src;
+    f.dst = BUF_OUT;
+    // compulsory HBM traffic of the fused pair: read the input once, write the result once
+    f.algo_bytes = a.algo_bytes;
+    char buf[320];
+    snprintf(buf, sizeof buf,
+             "fused row+col    %s L=%dx%d threads=%d smem=%d persistent grid=%u (%d CTAs/SM) groups=%d x %lld planes lag=%d "
+             "lines=%lld (last axis + next axis through L2)",
+             P->prec ? "fp64" : "fp32", a.ki->L, b.ki->L, fk->threads, fk->smem_bytes, f.grid, per_sm, f.n_groups, Pg, lag,
+             (long long)a.tp.n_tiles * a.ki->W);
+    f.desc = buf;
+    P->launches.erase(P->launches.begin(), P->launches.begin() + 2);
+    P->launches.insert(P->launches.begin(), f);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -498,6 +588,7 @@ static bool build_fast(Builder &B) {
         first = false;
     }
     if (first) return false;
+    try_fuse_first_two(B);
     // in place is safe when every pass reads and writes the same addresses tile by tile
     bool same = !P->real;
     for (int d = 0; d <= rank; ++d) same = same && (P->in_stride[d] == P->out_stride[d]);
@@ -685,6 +776,26 @@ static int run_launches(Plan *P, const void *in, void *out, int inverse) {
             tp.out = dst;
             tp.inverse = inverse;
             ce = launch_tile(ln.ki, ln.grid, P->stream, tp);
+        } else if (ln.kind == Launch::FUSED) {
+            FusedParams fp;
+            fp.a = ln.tp;
+            fp.a.in = src;
+            fp.a.out = dst;
+            fp.a.inverse = inverse;
+            fp.b = ln.tp_b;
+            fp.b.in = dst;
+            fp.b.out = dst;
+            fp.b.inverse = inverse;
+            fp.counters = ln.counters;
+            fp.tiles_a = ln.tiles_a;
+            fp.tiles_b = ln.tiles_b;
+            fp.n_groups = ln.n_groups;
+            fp.lag = ln.lag;
+            ce = cudaMemsetAsync(ln.counters, 0, sizeof(unsigned) * (size_t)(1 + ln.n_groups), P->stream);
+            if (ce == cudaSuccess) {
+                ln.fk->fn<<<ln.grid, ln.fk->threads, ln.fk->smem_bytes, P->stream>>>(fp);
+                ce = cudaGetLastError();
+            }
         } else {
             ce = P->prec ? launch_generic<double>(ln, src, dst, inverse, P->stream)
                          : launch_generic<float>(ln, src, dst, inverse, P->stream);
@@ -914,6 +1025,10 @@ int fftb200_get_launch_count(fftb200_handle plan, int *launches) {
     Plan *P = lookup_plan(plan);
     if (!P || !launches) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     *launches = (int)P->launches.size();
+    if (P->slab) {  // kernels one fused slab exec issues: pass 1, J x (pass 2 + pass 3), hand-shake kernels
+        const int J = P->slab->J;
+        *launches = 1 + 2 * J + (P->slab->G > 1 ? 2 + 2 * J : 0);
+    }
     return FFTB200_SUCCESS;
 }
 

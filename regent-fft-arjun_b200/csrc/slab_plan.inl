@@ -142,8 +142,13 @@ static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, in
         free_plan_resources(P.get());
         return code;
     };
-    // chunking of the contiguous index (multiples of 16 columns keep every segment >= 128 B)
-    if (chunks < 1) chunks = 1;
+    // chunking of the contiguous index (multiples of 16 columns keep every segment >= 128 B).
+    // chunks <= 0: automatic — 4 for single-CTA tiles (measured best on 2 x B200 at 512^3), 1 when the
+    // y-axis pass is a cluster kernel (a capped, persistent cluster pass loses more than the overlap wins)
+    if (chunks <= 0) {
+        const TileKernelInfo *k2 = find_tile_kernel(P->prec, V_CC_PEER, n[1]);
+        chunks = (G > 1 && k2 && k2->cluster == 1) ? 4 : 1;
+    }
     long long cw = (S->n2c + chunks - 1) / chunks;
     cw = (cw + 15) / 16 * 16;
     S->J = (int)((S->n2c + cw - 1) / cw);

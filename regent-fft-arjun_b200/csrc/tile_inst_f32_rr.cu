@@ -2,5 +2,6 @@
 #define TT float
 #define TT_IS_FLOAT 1
 #define VAR V_RR
+#define ROWONLY_VARIANT 1
 #define TABLE_NAME tile_table_f32_rr
 #include "tile_inst.inc"

@@ -2,5 +2,6 @@
 #define TT double
 #define TT_IS_DOUBLE 1
 #define VAR V_RR_R2C
+#define ROWONLY_VARIANT 1
 #define TABLE_NAME tile_table_f64_r2c
 #include "tile_inst.inc"

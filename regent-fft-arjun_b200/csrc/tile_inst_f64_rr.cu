@@ -2,5 +2,6 @@
 #define TT double
 #define TT_IS_DOUBLE 1
 #define VAR V_RR
+#define ROWONLY_VARIANT 1
 #define TABLE_NAME tile_table_f64_rr
 #include "tile_inst.inc"

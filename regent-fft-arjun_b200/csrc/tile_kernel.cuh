@@ -86,6 +86,13 @@ template <typename T, int L_, int R_, int W_, int VAR_> struct TileTraits {
     // index arithmetic then folds into immediate offsets.
     static constexpr bool SWIZZLED = LOAD_ROW || STORE_ROW || (W * (int)sizeof(cplx<T>) < 128);
     static constexpr int SWZ_BITS = !SWIZZLED ? 0 : (sizeof(cplx<T>) == 16 ? 3 : 4);
+    // two CTAs per SM (so that one tile's HBM phase overlaps the other's butterflies) whenever the tile's
+    // data fits 32 registers per thread: caps the kernel at 64 registers
+    static constexpr int MIN_CTAS_BY_THREADS = 1024 / THREADS < 1 ? 1 : (1024 / THREADS > 8 ? 8 : 1024 / THREADS);
+    static constexpr int MIN_CTAS_BY_SMEM = SMEM_BYTES == 0 ? 8 : (200 * 1024 / SMEM_BYTES < 1 ? 1 : 200 * 1024 / SMEM_BYTES);
+    static constexpr int MIN_CTAS = (int)sizeof(cplx<T>) * R > 128
+                                        ? 1
+                                        : (MIN_CTAS_BY_THREADS < MIN_CTAS_BY_SMEM ? MIN_CTAS_BY_THREADS : MIN_CTAS_BY_SMEM);
     static_assert(R * T_LINE == L, "R must divide L");
     static_assert(S == 1 || R_LAST <= R, "bad stage split");
 };
@@ -238,7 +245,9 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
         }
 }
 
-template <typename T, int L, int R, int W, int VAR>
+// DATA_CG: read the tile with ld.global.cg (L2-coherent).  Needed when the data was written earlier in the
+// SAME kernel by other SMs (fused two-axis pass): the read-only / L1 path could return stale lines.
+template <typename T, int L, int R, int W, int VAR, bool DATA_CG = false>
 __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int tile, unsigned char *smem_raw) {
     using TR = TileTraits<T, L, R, W, VAR>;
     using C = cplx<T>;
@@ -274,7 +283,10 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
 #pragma unroll
         for (int d = 0; d < R; ++d) {
             C x = mk<T>((T)0, (T)0);
-            if (ok) x = ld_cplx<T>(src + (long long)(d * T_LINE) * p.in_ls);
+            if (ok) {
+                if constexpr (DATA_CG) x = __ldcg(src + (long long)(d * T_LINE) * p.in_ls);
+                else x = ld_cplx<T>(src + (long long)(d * T_LINE) * p.in_ls);
+            }
             if (inv) { T s = x.x; x.x = x.y; x.y = s; }
             v[d] = x;
         }
@@ -334,12 +346,90 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
 // CTA owns one tile; a smaller grid makes the pass persistent on a bounded number of SMs, which is how
 // the slab plans keep an NVLink-bound exchange pass and an HBM-bound local pass running side by side.
 template <typename T, int L, int R, int W, int VAR>
-__global__ void __launch_bounds__(TileTraits<T, L, R, W, VAR>::THREADS)
+__global__ void __launch_bounds__(TileTraits<T, L, R, W, VAR>::THREADS, TileTraits<T, L, R, W, VAR>::MIN_CTAS)
 fft_tile_kernel(const TileParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         fft_tile_body<T, L, R, W, VAR>(p, tile, smem_raw);
         if (TileTraits<T, L, R, W, VAR>::NEED_SMEM && tile + (int)gridDim.x < p.n_tiles) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused two-axis pass: the contiguous-axis pass (A, ROW/ROW) and the next strided-axis pass (B, COL/COL,
+// in place on A's output) of a multi-dimensional transform in ONE persistent kernel, ordered so that B
+// reads A's output while it is still in the 126 MB L2: the intermediate never has to come back from HBM.
+//
+// Work is cut into groups of whole planes.  CTAs draw tickets from a global counter; the ticket order is
+//   A(0) A(1) .. A(lag-1) | A(lag) B(0) | A(lag+1) B(1) | ... | B(n_groups-1)
+// A(g)/B(g) = the tiles of group g.  A tile of B(g) waits (acquire-spin on done[g]) until all tiles of
+// A(g) have been stored; those tiles were handed out at least `lag` slots earlier, i.e. to CTAs that are
+// running or finished, so the wait cannot deadlock and is normally already satisfied.
+// ---------------------------------------------------------------------------------------------
+struct FusedParams {
+    TileParams a, b;
+    unsigned *counters;  // [0] ticket dispenser, [1 + g] finished A tiles of group g (zeroed before the launch)
+    int tiles_a, tiles_b;  // per group
+    int n_groups, lag;
+};
+
+template <typename T, int LA, int RA, int WA, int LB, int RB, int WB>
+__global__ void __launch_bounds__(TileTraits<T, LA, RA, WA, V_RR>::THREADS, TileTraits<T, LA, RA, WA, V_RR>::MIN_CTAS)
+fft_fused_ab_kernel(const FusedParams p) {
+    using TA = TileTraits<T, LA, RA, WA, V_RR>;
+    using TB = TileTraits<T, LB, RB, WB, V_CC>;
+    static_assert(TA::THREADS == TB::THREADS, "both passes must use the same CTA shape");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_ticket[2];
+    const int per_slot = p.tiles_a + p.tiles_b;
+    const int head = p.lag * p.tiles_a;                          // tickets of the A-only slots
+    const int mid = (p.n_groups - p.lag) * per_slot;             // slots with both
+    const int total = p.n_groups * per_slot;
+    int cur = 0;
+    if (threadIdx.x == 0) s_ticket[0] = (int)atomicAdd(p.counters, 1u);
+    __syncthreads();
+    for (;;) {
+        const int ticket = s_ticket[cur];
+        if (ticket >= total) break;
+        // draw the next ticket now; its L2 round trip hides behind this tile (consumed at the loop end)
+        unsigned next_ticket = 0;
+        if (threadIdx.x == 0) next_ticket = atomicAdd(p.counters, 1u);
+        bool is_b;
+        int g, t;
+        if (ticket < head) {
+            is_b = false; g = ticket / p.tiles_a; t = ticket - g * p.tiles_a;
+        } else if (ticket < head + mid) {
+            const int r = ticket - head;
+            const int slot = r / per_slot, q = r - slot * per_slot;
+            if (q < p.tiles_a) { is_b = false; g = p.lag + slot; t = q; }
+            else { is_b = true; g = slot; t = q - p.tiles_a; }
+        } else {
+            const int r = ticket - head - mid;
+            is_b = true; g = (p.n_groups - p.lag) + r / p.tiles_b; t = r % p.tiles_b;
+        }
+        if (!is_b) {
+            fft_tile_body<T, LA, RA, WA, V_RR, false>(p.a, g * p.tiles_a + t, smem_raw);
+            __syncthreads();  // all stores of the tile issued
+            // the last warp publishes the tile; warp 0 is free to go on with the next ticket
+            if (threadIdx.x == TA::THREADS - 1) {
+                __threadfence();
+                atomicAdd(p.counters + 1 + g, 1u);
+            }
+        } else {
+            if (threadIdx.x == 0) {
+                const unsigned *f = p.counters + 1 + g;
+                unsigned v;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                    if (v < (unsigned)p.tiles_a) __nanosleep(100);
+                } while (v < (unsigned)p.tiles_a);
+            }
+            __syncthreads();
+            fft_tile_body<T, LB, RB, WB, V_CC, true>(p.b, g * p.tiles_b + t, smem_raw);
+        }
+        if (threadIdx.x == 0) s_ticket[cur ^ 1] = (int)next_ticket;
+        __syncthreads();  // next ticket visible; shared memory of this tile free
+        cur ^= 1;
     }
 }
 
@@ -379,9 +469,7 @@ __device__ __forceinline__ void dsmem_st(unsigned addr, float2 v) {
 // (decimation in frequency: X[k1 + CL*k'] = DFT_LL( DFT_CL_d(x[d*LL+j])(k1) * w_L^(j*k1) )[k'])
 // ---------------------------------------------------------------------------------------------
 template <typename T, int LL, int CL, int R, int W, int VAR>
-__global__ void __launch_bounds__(TileTraits<T, LL, R, W, VAR>::THREADS,
-                                  (TileTraits<T, LL, R, W, VAR>::SMEM_BYTES <= 100 * 1024 &&
-                                   TileTraits<T, LL, R, W, VAR>::THREADS * 2 <= 1024 && sizeof(T) * R <= 64) ? 2 : 1)
+__global__ void __launch_bounds__(TileTraits<T, LL, R, W, VAR>::THREADS, TileTraits<T, LL, R, W, VAR>::MIN_CTAS)
 fft_cluster_kernel(const TileParams p) {
     namespace cg = cooperative_groups;
     using TR = TileTraits<T, LL, R, W, VAR>;
@@ -409,7 +497,7 @@ fft_cluster_kernel(const TileParams p) {
 
     // every CTA of the cluster must be running before its shared memory is written remotely: arrive now,
     // wait just before the first scatter (the HBM loads in between hide the barrier)
-    cluster.barrier_arrive();
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     bool first = true;
     for (int tile = (int)blockIdx.x / CL; tile < p.n_tiles; tile += n_clusters) {
         const int o = tile / p.tiles_per_outer;
@@ -431,7 +519,7 @@ fft_cluster_kernel(const TileParams p) {
                     if (inv) { T s = x.x; x.x = x.y; x.y = s; }
                     v[it * CL + d] = x;
                 }
-            if (first) { cluster.barrier_wait(); first = false; }
+            if (first) { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); first = false; }
 #pragma unroll
             for (int it = 0; it < NI; ++it) {
                 const int j = j0 + it * T_LINE;
@@ -458,7 +546,7 @@ fft_cluster_kernel(const TileParams p) {
         // persistent launch: nobody may scatter the next tile into a CTA that still works on this one
         if (tile + n_clusters < p.n_tiles) cluster.sync();
     }
-    if (first) cluster.barrier_wait();
+    if (first) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 }  // namespace fftb200

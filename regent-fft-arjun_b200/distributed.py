@@ -89,7 +89,7 @@ class SlabFFT3D:
     double->complex64 (D2Z), float->complex32 (R2C).  execute() is collective.
     """
 
-    def __init__(self, shape, dtype_in, dtype_out=None, rank=None, world=None, device=None, mode="p2p", chunks=4,
+    def __init__(self, shape, dtype_in, dtype_out=None, rank=None, world=None, device=None, mode="p2p", chunks=0,
                  group=None, engine=None):
         from . import _dtype, complex32, complex64
         self.shape = tuple(int(v) for v in shape)
@@ -150,14 +150,12 @@ class SlabFFT3D:
 
     @property
     def launches_per_step(self) -> int:
-        if self.mode == "p2p":
-            j = slab_chunks(self.local_out_shape[2], self.chunks)
-            sync = (2 + 2 * j) if self.world > 1 else 0
-            return 1 + 2 * j + sync
+        if self.mode == "p2p" and hasattr(self.engine, "h"):
+            return _lib.launch_count(self.engine.h)
         return 3
 
     def describe(self) -> str:
-        ex = ("y-axis FFT pass stores into peer HBM over NVLink (fused exchange, %d chunks)" % self.chunks
+        ex = ("y-axis FFT pass stores into peer HBM over NVLink (fused exchange, chunks=%s)" % (self.chunks or "auto")
               if self.mode == "p2p" else "NCCL all_to_all_single between the y- and z-axis passes")
         return f"slab x{self.world}: dim0 -> dim1 (transposed-out), {ex}"
 

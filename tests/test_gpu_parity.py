@@ -382,7 +382,7 @@ def test_c4_512cubed_properties(L, oracle):
     N = n ** 3
     tol = oracle.tolerance(N, False)
     h = L.plan_many(3, [n, n, n], None, 0, 0, None, 0, 0, L.Z2Z, 1)
-    assert L.launch_count(h) == 3
+    assert L.launch_count(h) in (2, 3)          # 2 when the x and y passes are fused through L2
     g = torch.Generator(device="cuda").manual_seed(1234)
     a = torch.rand(n, n, n, 2, dtype=torch.float64, device="cuda", generator=g).sub_(0.5)
     a = torch.view_as_complex(a)
@@ -445,7 +445,7 @@ def test_c4_subcube_against_oracle_128(L, oracle):
     x = oracle.synth((128, 128, 128), np.complex128, 540)
     got, desc = gpu_fft(L, "z2z", x, (128, 128, 128))
     assert oracle.rel_l2(got, cpu_fft(oracle, "z2z", x, (128, 128, 128))) <= oracle.tolerance(128 ** 3, False)
-    assert desc.count("\n") == 3
+    assert desc.count("\n") in (2, 3)
 
 
 def test_c2_4096sq_r2c_properties(L, oracle):
@@ -535,7 +535,43 @@ def test_native_library_is_the_one_running(fft, L):
     needed = subprocess.run(["readelf", "-d", L.LIB_PATH], capture_output=True, text=True).stdout
     assert "NEEDED" in needed and "cufft" not in needed.lower() and "nccl" not in needed.lower(), needed
     h = L.plan_many(3, [512, 512, 512], None, 0, 0, None, 0, 0, L.Z2Z, 1)
-    assert L.launch_count(h) == 3 and L.work_size(h) == 0
-    total = sum(L.launch_bytes(h, i) for i in range(3))
-    assert total == 3 * 2 * 512 ** 3 * 16                              # pass-model bytes of SURVEY.md §8d
+    nl = L.launch_count(h)
+    assert nl in (2, 3) and L.work_size(h) == 0
+    total = sum(L.launch_bytes(h, i) for i in range(nl))
+    # compulsory HBM bytes: one read + one write of 512^3 complex64 per launch (a fused launch covers two
+    # axis passes of SURVEY.md §8d's pass model with the traffic of one)
+    assert total == nl * 2 * 512 ** 3 * 16
     L.destroy(h)
+
+
+def test_fused_xy_pass_is_bit_identical_to_separate_passes(L, oracle):
+    """the L2-fused x+y kernel runs the same butterflies as the two separate passes"""
+    for kind, shape, batch in [("z2z", (64, 128, 128), 1), ("c2c", (32, 256, 256), 1), ("z2z", (256, 256), 16),
+                               ("z2z", (16, 256, 256), 1), ("c2c", (32, 128, 128), 2)]:
+        ftype, dt_in, _ = _kinds(L)[kind]
+        full = ((batch,) if batch > 1 else ()) + shape
+        x = torch.from_numpy(oracle.synth(full, dt_in, 700)).cuda()
+        outs, descs = [], []
+        for fuse in ("1", "0"):
+            os.environ["FFTB200_FUSE"] = fuse
+            h = L.plan_many(len(shape), list(shape), None, 0, 0, None, 0, 0, ftype, batch)
+            y = torch.zeros_like(x)
+            for _ in range(2):
+                L.execute(h, ftype, x.data_ptr(), y.data_ptr())
+            torch.cuda.synchronize()
+            descs.append(L.describe(h))
+            L.destroy(h)
+            outs.append(y)
+        os.environ["FFTB200_FUSE"] = "1"
+        assert "fused" in descs[0] and "fused" not in descs[1], descs
+        assert torch.equal(outs[0], outs[1]), (kind, shape)
+        want = cpu_fft(oracle, kind, x.cpu().numpy(), shape, batch)
+        assert oracle.rel_l2(outs[0].cpu().numpy(), want) <= oracle.tolerance(int(np.prod(shape)), kind == "c2c")
+        # in place through the fused kernel
+        h = L.plan_many(len(shape), list(shape), None, 0, 0, None, 0, 0, ftype, batch)
+        xi = x.clone()
+        L.execute(h, ftype, xi.data_ptr(), xi.data_ptr())
+        torch.cuda.synchronize()
+        L.destroy(h)
+        os.environ.pop("FFTB200_FUSE")
+        assert torch.equal(xi, outs[0]), (kind, shape, "in place")
