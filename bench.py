@@ -315,21 +315,47 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> int:
         roof = dplan.roofline(ms_step, peak, peak_src)
 
     # ---- e2e: same metric through the C ABI with HOST buffers (H2D + transform + D2H in the timed region) ----
+    # A caller that streams batches keeps two transforms in flight (two plans on two streams, each call
+    # stream-ordered like cufftExec): step k's device->host copy then overlaps step k+1's host->device copy
+    # on the full-duplex host link.  Every step still copies its own input in and its own result out.
+    e_steps = max(4, min(steps, 8))
     if world == 1:
-        hx = torch.empty(SHAPE, dtype=torch.complex128, pin_memory=True)
-        hy = torch.empty(SHAPE, dtype=torch.complex128, pin_memory=True)
-        hx.copy_(x)
-        e_steps = max(2, min(steps, 5))
-        e2e_step = lambda: L.execute(h, L.Z2Z, hx.data_ptr(), hy.data_ptr())
+        npipe = 2
+        hx = [torch.empty(SHAPE, dtype=torch.complex128, pin_memory=True) for _ in range(npipe)]
+        hy = [torch.empty(SHAPE, dtype=torch.complex128, pin_memory=True) for _ in range(npipe)]
+        for b in hx:
+            b.copy_(x)
+        pipes = [torch.cuda.Stream(device=dev) for _ in range(npipe)]
+        eplans = [L.plan_many(3, list(SHAPE), None, 0, 0, None, 0, 0, L.Z2Z, 1) for _ in range(npipe)]
+        for hp, st in zip(eplans, pipes):
+            L.set_stream(hp, st.cuda_stream)
+        done = [torch.cuda.Event() for _ in range(npipe)]
+
+        def e2e_run(nsteps):
+            for st in pipes:
+                st.wait_stream(stream)
+            for k in range(nsteps):
+                i = k % npipe
+                L.execute(eplans[i], L.Z2Z, hx[i].data_ptr(), hy[i].data_ptr())
+            for st, ev in zip(pipes, done):
+                ev.record(st)
+                stream.wait_event(ev)
+
         h2d = d2h = N_TOTAL * ELT
+        e2e_path = ("fftb200_exec_z2z(host pinned in, host pinned out), 2 plans on 2 streams alternating: "
+                    "staged H2D, passes on HBM, D2H; consecutive steps' copies overlap")
     else:
-        e_steps = max(2, min(steps, 5))
         e2e_step, h2d, d2h = dplan.make_host_step(x)
-    e2e_step()
+
+        def e2e_run(nsteps):
+            for _ in range(nsteps):
+                e2e_step()
+
+        e2e_path = "per-rank slab: pinned host -> HBM, slab transform, HBM -> pinned host"
+    e2e_run(2)
     barrier()
     e0.record(stream)
-    for _ in range(e_steps):
-        e2e_step()
+    e2e_run(e_steps)
     e1.record(stream)
     barrier()
     e_ms = e0.elapsed_time(e1)
@@ -340,11 +366,14 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> int:
     e_ms /= e_steps
     e2e = {"value": FLOPS / (e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
            "d2h_bytes_per_step": d2h * world if world > 1 else d2h, "ms_per_step": e_ms, "steps": e_steps,
-           "host_link_GB/s_each_way": (h2d + d2h) / (e_ms * 1e-3) / 1e9 / 2,
-           "path": "fftb200_exec_z2z(host pinned in, host pinned out): staged H2D, 3 passes on HBM, D2H"}
+           "host_link_GB/s_each_way": h2d / (e_ms * 1e-3) / 1e9, "path": e2e_path}
     if world == 1:
-        # the device result of the host-buffer call equals the resident-input call on the same data
-        assert torch.equal(hy.to(dev), y), "e2e result differs from the resident-input result"
+        # the host-buffer calls give the same bits as the resident-input call on the same data
+        for b in hy:
+            assert torch.equal(b.to(dev), y), "e2e result differs from the resident-input result"
+        for hp in eplans:
+            L.destroy(hp)
+        del hx, hy
 
     # ---- cpu baseline: the reference's FFTW on this box's host cores (rank 0, N=1 only) -----------------
     cpu = None

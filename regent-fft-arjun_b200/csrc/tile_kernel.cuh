@@ -218,23 +218,61 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
     const bool ok = (i0 + wl) < p.n_inner;
     const long long off = o1 * p.out_os1 + o2 * p.out_os2 + (long long)(i0 + wl) * p.out_is;
     C *dst = reinterpret_cast<C *>(p.out) + off;
+    if constexpr (VAR == V_CC_TW) {
+        // four-step twiddles by recurrence in fp64: the exponent of w_N is affine in (b, q),
+        //   m = i*(kadd + kmul*ul) + b*(i*kmul*T_LINE) + q*(i*kmul*L/RL),
+        // so a few two-level table lookups per thread replace two per point (the table traffic through
+        // L1/L2 was 4x the pass's HBM bytes in fp32).  fp32 data: recurrence over b and q (<= B+RL fp64
+        // multiplications deep, error ~1e-15); fp64 data: one lookup per b, recurrence over q only
+        // (<= RL-1 <= 7 multiplications: a few eps on the twiddle, far inside the 10*log2(N)*eps budget).
+        constexpr bool RECUR_B = sizeof(T) == 4;
+        auto lookup = [&](long long m) {
+            const double2 wh = __ldg(p.tw4_hi + (m >> p.tw4_shift));
+            const double2 wlw = __ldg(p.tw4_lo + (m & p.tw4_mask));
+            double2 r;
+            r.x = wh.x * wlw.x - wh.y * wlw.y;
+            r.y = wh.x * wlw.y + wh.y * wlw.x;
+            return r;
+        };
+        auto mul = [](double2 a, double2 b2) {
+            double2 r;
+            r.x = a.x * b2.x - a.y * b2.y;
+            r.y = a.x * b2.y + a.y * b2.x;
+            return r;
+        };
+        const long long i = i0 + wl;
+        double2 wb = lookup(i * (long long)(kadd + kmul * ul));
+        double2 sb, sq;
+        sb.x = sq.x = 1.0;
+        sb.y = sq.y = 0.0;
+        if (B > 1 && RECUR_B) sb = lookup(i * (long long)(kmul * T_LINE));
+        if (RL > 1) sq = lookup(i * (long long)(kmul * (L / RL)));
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            double2 wq = wb;
+#pragma unroll
+            for (int q = 0; q < RL; ++q) {
+                const int k = kadd + kmul * ((ul + b * T_LINE) + q * (L / RL));
+                C x = v[b * RL + q];
+                const double xr = (double)x.x * wq.x - (double)x.y * wq.y;
+                const double xi = (double)x.x * wq.y + (double)x.y * wq.x;
+                x.x = (T)xr; x.y = (T)xi;
+                if (inv) { T s2 = x.x; x.x = x.y; x.y = s2; }
+                if (ok) dst[(long long)k * p.out_ls] = x;
+                if (q + 1 < RL) wq = mul(wq, sq);
+            }
+            if (b + 1 < B) {
+                if constexpr (RECUR_B) wb = mul(wb, sb);
+                else wb = lookup(i * (long long)(kadd + kmul * (ul + (b + 1) * T_LINE)));
+            }
+        }
+    } else {
 #pragma unroll
     for (int b = 0; b < B; ++b)
 #pragma unroll
         for (int q = 0; q < RL; ++q) {
             const int k = kadd + kmul * ((ul + b * T_LINE) + q * (L / RL));
             C x = v[b * RL + q];
-            if constexpr (VAR == V_CC_TW) {
-                // four-step twiddle w_N^(i*k), N = L * n_inner; two-level fp64 table
-                const long long m = (long long)(i0 + wl) * k;
-                const double2 wh = __ldg(p.tw4_hi + (m >> p.tw4_shift));
-                const double2 wlw = __ldg(p.tw4_lo + (m & p.tw4_mask));
-                const double wr = wh.x * wlw.x - wh.y * wlw.y;
-                const double wi = wh.x * wlw.y + wh.y * wlw.x;
-                const double xr = (double)x.x * wr - (double)x.y * wi;
-                const double xi = (double)x.x * wi + (double)x.y * wr;
-                x.x = (T)xr; x.y = (T)xi;
-            }
             if (inv) { T s = x.x; x.x = x.y; x.y = s; }
             if constexpr (VAR == V_CC_PEER) {
                 C *pd = reinterpret_cast<C *>(p.peer[k >> p.peer_shift]) + off;
@@ -243,6 +281,7 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
                 if (ok) dst[(long long)k * p.out_ls] = x;
             }
         }
+    }
 }
 
 // DATA_CG: read the tile with ld.global.cg (L2-coherent).  Needed when the data was written earlier in the
