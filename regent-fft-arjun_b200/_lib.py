@@ -11,7 +11,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfft_b200.so")
+# FFTB200_LIB_PATH: tuning experiments only (A/B of differently compiled builds); the default is the in-tree build
+LIB_PATH = os.environ.get("FFTB200_LIB_PATH") or os.path.join(_HERE, "libfft_b200.so")
 
 # enums of include/fft_b200.h
 R2C, C2C, D2Z, Z2Z = 0x2A, 0x29, 0x6A, 0x69

@@ -55,6 +55,8 @@ struct TileParams {
     long long in_ls, in_is, in_os1, in_os2;
     long long out_ls, out_is, out_os1, out_os2;
     int n_tiles;   // tiles of the whole pass (a CTA loops over tile = blockIdx.x + k * gridDim.x)
+    int prefetch_tiles;  // > 0: every CTA asks L2 to prefetch the input of tile + prefetch_tiles (the tile the
+                         // CTA slot it occupies will run next), decoupling HBM latency from SM occupancy
     int n_inner;   // lines along the inner index
     int n_o2;      // outer index o = o1*n_o2 + o2
     int tiles_per_outer;
@@ -110,6 +112,26 @@ template <int BITS, int TOTAL_BITS> __device__ __forceinline__ int swz_fold(int 
 }
 
 template <typename T> __device__ __forceinline__ cplx<T> ld_cplx(const cplx<T> *p) { return __ldg(p); }
+// Tile data is touched exactly once per pass: load it evict-first / store it streaming so that it does not
+// push the twiddle tables (re-read by every CTA) out of L1.
+// (measured on B200: streaming hints make the 512^3 passes 5-10 % slower, so they stay off)
+#ifndef FFTB200_STREAMING
+#define FFTB200_STREAMING 0
+#endif
+template <typename T> __device__ __forceinline__ cplx<T> ld_data(const cplx<T> *p) {
+#if FFTB200_STREAMING
+    return __ldcs(p);
+#else
+    return __ldg(p);
+#endif
+}
+template <typename T> __device__ __forceinline__ void st_data(cplx<T> *p, cplx<T> v) {
+#if FFTB200_STREAMING
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // All radix stages of one tile.  In: thread (w1, u1) holds x[u1 + d*T_LINE], d < R, of line w1 in v[].
@@ -258,7 +280,7 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
                 const double xi = (double)x.x * wq.y + (double)x.y * wq.x;
                 x.x = (T)xr; x.y = (T)xi;
                 if (inv) { T s2 = x.x; x.x = x.y; x.y = s2; }
-                if (ok) dst[(long long)k * p.out_ls] = x;
+                if (ok) st_data<T>(dst + (long long)k * p.out_ls, x);
                 if (q + 1 < RL) wq = mul(wq, sq);
             }
             if (b + 1 < B) {
@@ -278,7 +300,7 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
                 C *pd = reinterpret_cast<C *>(p.peer[k >> p.peer_shift]) + off;
                 if (ok) pd[(long long)(k & p.peer_mask) * p.out_ls] = x;
             } else {
-                if (ok) dst[(long long)k * p.out_ls] = x;
+                if (ok) st_data<T>(dst + (long long)k * p.out_ls, x);
             }
         }
     }
@@ -311,6 +333,37 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
     const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);
     const bool inv = p.inverse != 0;
 
+    // ------------------------------------------------------------------ L2 prefetch of a future tile
+    if (p.prefetch_tiles > 0) {
+        const int ft = tile + p.prefetch_tiles;
+        if (ft < p.n_tiles) {
+            const int fo = ft / p.tiles_per_outer;
+            const int fi0 = (ft - fo * p.tiles_per_outer) * W;
+            const int fo1 = fo / p.n_o2, fo2 = fo - fo1 * p.n_o2;
+            if (fi0 + W <= p.n_inner) {  // whole tiles only: never touch addresses past the array
+                const C *fin = reinterpret_cast<const C *>(p.in) + fo1 * p.in_os1 + fo2 * p.in_os2 + (long long)fi0 * p.in_is;
+                constexpr int ELT = (int)sizeof(C);
+                if constexpr (TR::LOAD_ROW) {
+                    // W lines of L contiguous elements each
+                    constexpr int CH_LINE = (L * ELT + 127) / 128;  // 128-byte chunks per line
+                    for (int ch = t; ch < W * CH_LINE; ch += TR::THREADS) {
+                        const int wl2 = ch / CH_LINE, cc = ch - wl2 * CH_LINE;
+                        const char *a = reinterpret_cast<const char *>(fin + (long long)wl2 * p.in_is) + cc * 128;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                    }
+                } else {
+                    // L rows of W contiguous elements each
+                    constexpr int CH_ROW = (W * ELT + 127) / 128;
+                    for (int ch = t; ch < L * CH_ROW; ch += TR::THREADS) {
+                        const int r = ch / CH_ROW, cc = ch - r * CH_ROW;
+                        const char *a = reinterpret_cast<const char *>(fin + (long long)r * p.in_ls) + cc * 128;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                    }
+                }
+            }
+        }
+    }
+
     C v[R];
 
     // ------------------------------------------------------------------ stage 1: HBM -> registers
@@ -324,7 +377,7 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
             C x = mk<T>((T)0, (T)0);
             if (ok) {
                 if constexpr (DATA_CG) x = __ldcg(src + (long long)(d * T_LINE) * p.in_ls);
-                else x = ld_cplx<T>(src + (long long)(d * T_LINE) * p.in_ls);
+                else x = ld_data<T>(src + (long long)(d * T_LINE) * p.in_ls);
             }
             if (inv) { T s = x.x; x.x = x.y; x.y = s; }
             v[d] = x;
@@ -554,7 +607,7 @@ fft_cluster_kernel(const TileParams p) {
 #pragma unroll
                 for (int d = 0; d < CL; ++d) {
                     C x = mk<T>((T)0, (T)0);
-                    if (ok) x = ld_cplx<T>(src + (long long)(d * LL + it * T_LINE) * p.in_ls);
+                    if (ok) x = ld_data<T>(src + (long long)(d * LL + it * T_LINE) * p.in_ls);
                     if (inv) { T s = x.x; x.x = x.y; x.y = s; }
                     v[it * CL + d] = x;
                 }
