@@ -10,6 +10,7 @@
 //
 //   rank r holds   in  [n0/G][n1][n2]      (slab r of dim 0, row-major)
 //   pass 1         x-axis FFT (or fused r2c)              in  -> tmp [n0/G][n1][n2c]     HBM
+//                  (tmp and recv rows are padded to whole 128-byte lines internally)
 //   pass 2         y-axis FFT whose STORE is the exchange: output line index k1 belongs to rank
 //                  k1 / (n1/G); it is written straight into that rank's receive buffer
 //                  recv_d [n1/G][n0][n2c] at [k1 % (n1/G)][r*n0/G + p][i]
@@ -25,9 +26,11 @@
 
 struct SlabState {
     int rank = 0, G = 1, J = 1;
-    long long n0 = 0, n1 = 0, n2 = 0, n2c = 0, n0l = 0, n1l = 0;
-    void *tmp = nullptr;   // [n0l][n1][n2c]
-    void *area = nullptr;  // exchange area: recv [n1l][n0][n2c], then flags
+    long long n0 = 0, n1 = 0, n2 = 0, n2c = 0, n2p = 0, n0l = 0, n1l = 0;
+    // internal slabs use a row pitch n2p = n2c rounded up to a whole number of 128-byte lines, so that the
+    // peer stores of an R2C exchange (n2c = n2/2+1 columns) stay line-aligned on NVLink
+    void *tmp = nullptr;   // [n0l][n1][n2p]
+    void *area = nullptr;  // exchange area: recv [n1l][n0][n2p], then flags
     size_t recv_bytes = 0, area_bytes = 0, flags_off = 0;
     void *peer_area[MAX_PEERS] = {};
     bool peer_mapped[MAX_PEERS] = {};
@@ -131,11 +134,15 @@ static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, in
     S->G = G;
     S->n0 = n[0]; S->n1 = n[1]; S->n2 = n[2];
     S->n2c = P->real ? n[2] / 2 + 1 : n[2];
+    {
+        const long long per_line = P->prec ? 8 : 16;  // complex elements per 128 bytes
+        S->n2p = (S->n2c + per_line - 1) / per_line * per_line;
+    }
     S->n0l = n[0] / G;
     S->n1l = n[1] / G;
     P->n[0] = S->n0l; P->n[1] = n[1]; P->n[2] = n[2];
     const size_t ce = P->prec ? 16 : 8;
-    const long long vol = S->n0l * S->n1 * S->n2c;  // == n1l * n0 * n2c
+    const long long vol = S->n0l * S->n1 * S->n2p;  // == n1l * n0 * n2p
     Builder B;
     B.P = P.get();
     auto fail = [&](int code) {
@@ -167,12 +174,12 @@ static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, in
     {
         std::vector<Level> lv;
         if (P->real) {
-            lv.push_back({S->n0l * S->n1, S->n2 / 2, S->n2c});  // rows; input pitch in complex pairs
+            lv.push_back({S->n0l * S->n1, S->n2 / 2, S->n2p});  // rows; input pitch in complex pairs
             if (S->n2 & 1) return fail(FFTB200_INVALID_SIZE);
             if (!add_tile_pass(B, V_RR_R2C, (int)(S->n2 / 2), 1, 1, lv, BUF_IN, BUF_WORK0, 0, "slab pass 1: x axis r2c"))
                 return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
         } else {
-            lv.push_back({S->n0l * S->n1, S->n2, S->n2c});
+            lv.push_back({S->n0l * S->n1, S->n2, S->n2p});
             if (!add_tile_pass(B, V_RR, (int)S->n2, 1, 1, lv, BUF_IN, BUF_WORK0, 0, "slab pass 1: x axis"))
                 return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
         }
@@ -186,13 +193,13 @@ static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, in
     // ---- pass 2, p2p: y axis on chunk j, tmp -> peers' recv [n1l][n0][n2c] at plane r*n0l + p
     for (int j = 0; j < S->J; ++j) {
         const long long c0 = j * cw, w = std::min(cw, S->n2c - c0);
-        std::vector<Level> lv = {{w, 1, 1}, {S->n0l, S->n1 * S->n2c, S->n2c}};
-        if (!add_tile_pass(B, V_CC_PEER, (int)S->n1, S->n2c, S->n0 * S->n2c, lv, BUF_WORK0, BUF_OUT, 0,
+        std::vector<Level> lv = {{w, 1, 1}, {S->n0l, S->n1 * S->n2p, S->n2p}};
+        if (!add_tile_pass(B, V_CC_PEER, (int)S->n1, S->n2p, S->n0 * S->n2p, lv, BUF_WORK0, BUF_OUT, 0,
                            "slab pass 2: y axis, store = exchange (peer memory)"))
             return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
         Launch &ln = P->launches.back();
         ln.in_off = c0;
-        ln.out_off = (long long)rank * S->n0l * S->n2c + c0;
+        ln.out_off = (long long)rank * S->n0l * S->n2p + c0;
         set_peer(ln);
         // The exchange pass is NVLink-bound, not SM-bound: when it is pipelined against the z-axis pass
         // keep it persistent on a bounded number of CTAs so that the HBM-bound pass finds free SMs.
@@ -205,8 +212,8 @@ static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, in
     // ---- pass 3, p2p: z axis on chunk j, recv [n1l][n0][n2c] -> out (same layout)
     for (int j = 0; j < S->J; ++j) {
         const long long c0 = j * cw, w = std::min(cw, S->n2c - c0);
-        std::vector<Level> lv = {{w, 1, 1}, {S->n1l, S->n0 * S->n2c, S->n0 * S->n2c}};
-        if (!add_tile_pass(B, V_CC, (int)S->n0, S->n2c, S->n2c, lv, BUF_WORK1, BUF_OUT, 0, "slab pass 3: z axis"))
+        std::vector<Level> lv = {{w, 1, 1}, {S->n1l, S->n0 * S->n2p, S->n0 * S->n2c}};
+        if (!add_tile_pass(B, V_CC, (int)S->n0, S->n2p, S->n2c, lv, BUF_WORK1, BUF_OUT, 0, "slab pass 3: z axis"))
             return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
         Launch &ln = P->launches.back();
         ln.in_off = c0;
@@ -215,8 +222,8 @@ static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, in
     }
     // ---- staged mode: pass 2 into the G blocks [d][n0l][n1l][n2c] of a send buffer ...
     {
-        std::vector<Level> lv = {{S->n2c, 1, 1}, {S->n0l, S->n1 * S->n2c, S->n1l * S->n2c}};
-        if (!add_tile_pass(B, V_CC_PEER, (int)S->n1, S->n2c, S->n2c, lv, BUF_WORK0, BUF_OUT, 0,
+        std::vector<Level> lv = {{S->n2c, 1, 1}, {S->n0l, S->n1 * S->n2p, S->n1l * S->n2c}};
+        if (!add_tile_pass(B, V_CC_PEER, (int)S->n1, S->n2p, S->n2c, lv, BUF_WORK0, BUF_OUT, 0,
                            "slab pass 2 (staged): y axis, store = pack into all-to-all blocks"))
             return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
         set_peer(P->launches.back());

@@ -575,3 +575,78 @@ def test_fused_xy_pass_is_bit_identical_to_separate_passes(L, oracle):
         L.destroy(h)
         os.environ.pop("FFTB200_FUSE")
         assert torch.equal(xi, outs[0]), (kind, shape, "in place")
+
+
+def test_concurrent_plans_from_many_threads(L, oracle):
+    """Legion runs one task per GPU processor concurrently in one process: plan creation,
+    execution on private streams and destruction from 8 host threads at once."""
+    import threading
+    shapes = [("z2z", (64, 64, 32)), ("c2c", (4096,)), ("d2z", (128, 256)), ("z2z", (1 << 16,)),
+              ("r2c", (32, 32, 64)), ("z2z", (12, 10)), ("c2c", (256, 64)), ("d2z", (2048,))]
+    inputs = [oracle.synth(sh, _kinds(L)[k][1], 900 + i) for i, (k, sh) in enumerate(shapes)]
+    wants = [cpu_fft(oracle, k, x, sh) for (k, sh), x in zip(shapes, inputs)]
+    errors = [None] * len(shapes)
+
+    def worker(i):
+        try:
+            kind, shape = shapes[i]
+            ftype, dt_in, dt_out = _kinds(L)[kind]
+            real = kind in ("d2z", "r2c")
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                xd = torch.from_numpy(inputs[i]).cuda()
+                oshape = shape[:-1] + (shape[-1] // 2 + 1,) if real else shape
+                yd = torch.zeros(oshape, dtype=_torch_dtype(dt_out), device="cuda")
+            st.synchronize()
+            for _ in range(5):
+                h = L.plan_many(len(shape), list(shape), None, 0, 0, None, 0, 0, ftype, 1)
+                L.set_stream(h, st.cuda_stream)
+                L.execute(h, ftype, xd.data_ptr(), yd.data_ptr())
+                st.synchronize()
+                L.destroy(h)
+            err = oracle.rel_l2(yd.cpu().numpy(), wants[i])
+            tol = oracle.tolerance(int(np.prod(shape)), kind in ("c2c", "r2c"))
+            errors[i] = None if err <= tol else f"{kind} {shape}: {err:.2e} > {tol:.2e}"
+        except Exception as ex:  # surfaced below
+            errors[i] = repr(ex)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(shapes))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert all(e is None for e in errors), errors
+
+
+def test_host_memory_regions_are_staged(L, oracle):
+    """The reference's mapper puts regions in zero-copy (pinned host) memory (test/test_mapper.cc:45-58):
+    host pointers — pinned or pageable — go through the plan's HBM staging and give the same bits."""
+    x = oracle.synth((64, 32, 128), np.complex128, 910)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.zeros_like(xd)
+    h = L.plan_many(3, [64, 32, 128], None, 0, 0, None, 0, 0, L.Z2Z, 1)
+    L.execute(h, L.Z2Z, xd.data_ptr(), yd.data_ptr())
+    hx = torch.from_numpy(x).pin_memory()
+    hy = torch.zeros(x.shape, dtype=torch.complex128).pin_memory()
+    L.execute(h, L.Z2Z, hx.data_ptr(), hy.data_ptr())
+    px = torch.from_numpy(x.copy())                          # pageable
+    py = torch.zeros(x.shape, dtype=torch.complex128)
+    L.execute(h, L.Z2Z, px.data_ptr(), py.data_ptr())
+    torch.cuda.synchronize()
+    L.destroy(h)
+    assert torch.equal(hy, yd.cpu()) and torch.equal(py, yd.cpu())
+    assert np.array_equal(hx.numpy(), x) and np.array_equal(px.numpy(), x)
+    # padded advanced layout from host memory: padding must survive the round trip
+    n, ie, oe, batch, idist, odist = [8, 16], [10, 20], [9, 24], 2, 207, 221
+    xs = oracle.synth((batch * idist,), np.complex128, 911)
+    want = np.full(batch * odist, -1 - 1j, dtype=np.complex128)
+    oracle.port_dft_many(n, batch, xs, ie, 1, idist, want, oe, 1, odist)
+    hxs = torch.from_numpy(xs).pin_memory()
+    hys = torch.full((batch * odist,), -1 - 1j, dtype=torch.complex128).pin_memory()
+    h = L.plan_many(2, n, ie, 1, idist, oe, 1, odist, L.Z2Z, batch)
+    L.execute(h, L.Z2Z, hxs.data_ptr(), hys.data_ptr())
+    torch.cuda.synchronize()
+    L.destroy(h)
+    got = hys.numpy()
+    assert oracle.rel_l2(got, want) <= oracle.tolerance(128, False)
+    assert np.array_equal(got == (-1 - 1j), want == (-1 - 1j))

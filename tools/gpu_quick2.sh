@@ -1,9 +1,5 @@
 #!/bin/bash
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/cufft_compare.py 2>&1 | python -c "
-import sys, json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print(d['kind'], d['shape'], d['b200_ms_min'], d['speedup_vs_cufft'], d['rel_l2_vs_cufft'], [p.split(' | ')[0] for p in d['passes']])
-"
-python bench.py --no-cpu-baseline | cut -c1-200
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29570 tools/slab_probe.py 1024 d2z quick 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tee gpurun_out/slab_probe_1024_d2z_2gpu.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 tools/slab_probe.py 512 z2z quick 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tee -a gpurun_out/slab_probe_1024_d2z_2gpu.log
