@@ -1045,7 +1045,7 @@ int fftb200_get_launch_count(fftb200_handle plan, int *launches) {
     if (!P || !launches) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     *launches = (int)P->launches.size();
     if (P->slab) {  // kernels one fused slab exec issues: pass 1, J x (pass 2 + pass 3), hand-shake kernels
-        const int J = P->slab->J;
+        const int J = P->real ? P->slab->J : P->slab->Jp;
         *launches = 1 + 2 * J + (P->slab->G > 1 ? 2 + 2 * J : 0);
     }
     return FFTB200_SUCCESS;

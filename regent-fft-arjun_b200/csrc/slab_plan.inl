@@ -19,6 +19,8 @@
 //                    - staged mode: recv_d are the G blocks of a local send buffer; the host runs any
 //                      all-to-all (NCCL) on it
 //   pass 3         z-axis FFT                             recv -> out [n1/G][n0][n2c]    HBM
+// Complex transforms run the fused path in the order y (+exchange), x, z instead (see slab_create): the x
+// axis is local on both sides of the exchange, and after it it can overlap the transfer chunk by chunk.
 //
 // p2p mode pipelines passes 2 and 3 over J chunks of the contiguous index i: chunk j of pass 3 starts
 // as soon as every rank has signalled chunk j of pass 2 (flags written into each peer's exchange area),
@@ -43,6 +45,10 @@ struct SlabState {
     int l_pass1 = -1, l_pre2 = -1, l_post3 = -1;
     std::vector<int> l_pass2, l_pass3;
     long long chunk_w = 0;
+    // complex transforms: y-first pipeline (see slab_exec_p2p): plane chunks
+    int Jp = 0;
+    std::vector<int> l_y, l_x;
+    int l_z = -1;
 };
 
 // flags: [kind 0 = "receive buffer free", 1.. = "chunk j written"][source rank] epochs
@@ -237,9 +243,54 @@ static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, in
             return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
         S->l_post3 = (int)P->launches.size() - 1;
     }
+    // ---- complex transforms, fused exchange: y axis first.  Before the exchange both x and y are local, after it
+    // both x and z are, so the x-axis pass can run on either side.  Doing y + exchange first, chunked over
+    // PLANES (each plane is independent), lets the x-axis pass of chunk c (rows of the receive slab whose plane
+    // lies in chunk c of any rank) start as soon as chunk c has arrived from every rank: it hides under the
+    // NVLink transfer of the following chunks, and only the z-axis pass is left after the exchange.
+    if (!P->real) {
+        int want = env_int("FFTB200_SLAB_PLANE_CHUNKS", 0);
+        if (want <= 0) want = (G > 1) ? 4 : 1;
+        long long Jp = 1;
+        while (Jp * 2 <= want && S->n0l % (Jp * 2) == 0) Jp *= 2;
+        S->Jp = (int)Jp;
+        const long long pc = S->n0l / Jp;
+        if (1 + S->Jp > 64) return fail(FFTB200_INVALID_VALUE);
+        for (int c = 0; c < S->Jp; ++c) {
+            std::vector<Level> lv = {{S->n2, 1, 1}, {pc, S->n1 * S->n2, S->n2p}};
+            if (!add_tile_pass(B, V_CC_PEER, (int)S->n1, S->n2, S->n0 * S->n2p, lv, BUF_IN, BUF_OUT, 0,
+                               "slab y axis (first), store = exchange (peer memory)"))
+                return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
+            Launch &ln = P->launches.back();
+            ln.in_off = (long long)c * pc * S->n1 * S->n2;
+            ln.out_off = ((long long)rank * S->n0l + (long long)c * pc) * S->n2p;
+            set_peer(ln);
+            if (G > 1 && S->Jp > 1 && ln.ki->cluster == 1) {  // (a capped cluster pass pays a cluster barrier per tile)
+                const unsigned cap = (unsigned)env_int("FFTB200_SLAB_P2_CTAS", 148);
+                if (cap > 0 && ln.grid > cap) ln.grid = std::max(1u, cap / ln.ki->cluster) * ln.ki->cluster;
+            }
+            S->l_y.push_back((int)P->launches.size() - 1);
+        }
+        for (int c = 0; c < S->Jp; ++c) {
+            std::vector<Level> lv = {{pc, S->n2p, S->n2p}, {(long long)G, S->n0l * S->n2p, S->n0l * S->n2p},
+                                     {S->n1l, S->n0 * S->n2p, S->n0 * S->n2p}};
+            if (!add_tile_pass(B, V_RR, (int)S->n2, 1, 1, lv, BUF_WORK1, BUF_WORK1, 0,
+                               "slab x axis on received planes (overlaps the exchange)"))
+                return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
+            Launch &ln = P->launches.back();
+            ln.in_off = ln.out_off = (long long)c * pc * S->n2p;
+            S->l_x.push_back((int)P->launches.size() - 1);
+        }
+        {
+            std::vector<Level> lv = {{S->n2, 1, 1}, {S->n1l, S->n0 * S->n2p, S->n0 * S->n2c}};
+            if (!add_tile_pass(B, V_CC, (int)S->n0, S->n2p, S->n2c, lv, BUF_WORK1, BUF_OUT, 0, "slab z axis (last)"))
+                return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
+            S->l_z = (int)P->launches.size() - 1;
+        }
+    }
     if (cudaStreamCreateWithFlags(&S->aux, cudaStreamNonBlocking) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
-    S->ev_chunk.assign(S->J, nullptr);
-    for (int j = 0; j < S->J; ++j)
+    S->ev_chunk.assign(std::max(S->J, S->Jp), nullptr);
+    for (int j = 0; j < std::max(S->J, S->Jp); ++j)
         if (cudaEventCreateWithFlags(&S->ev_chunk[j], cudaEventDisableTiming) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
     if (cudaEventCreateWithFlags(&S->ev_done, cudaEventDisableTiming) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
     for (int i = 0; i < 5; ++i)
@@ -271,6 +322,33 @@ static int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
     if (S->timing) cudaEventRecord(S->ev_t[0], st);
     // my receive buffer is free again (stream order: after my previous transform's pass 3)
     if (S->G > 1) slab_signal_kernel<<<1, 32, 0, st>>>(peers, S->G, S->rank, 0, epoch);
+    if (!P->real) {
+        // y axis + exchange (plane chunks) -> x axis on arrived chunks (second stream) -> z axis
+        if (S->G > 1) slab_wait_kernel<<<1, 32, 0, st>>>(slab_flags(S, S->rank), S->G, 0, epoch);
+        if (S->timing) cudaEventRecord(S->ev_t[1], st);
+        for (int c = 0; c < S->Jp; ++c) {
+            int rc2 = slab_launch(P, S->l_y[c], in, nullptr, recv, inverse, st);
+            if (rc2) return rc2;
+            if (S->G > 1) slab_signal_kernel<<<1, 32, 0, st>>>(peers, S->G, S->rank, 1 + c, epoch);
+            if (c == S->Jp - 1 && S->timing) cudaEventRecord(S->ev_t[2], st);
+            cudaStream_t sx = (S->Jp > 1) ? S->aux : st;
+            if (S->Jp > 1) {
+                cudaEventRecord(S->ev_chunk[c], st);
+                cudaStreamWaitEvent(sx, S->ev_chunk[c], 0);
+            }
+            if (S->G > 1) slab_wait_kernel<<<1, 32, 0, sx>>>(slab_flags(S, S->rank), S->G, 1 + c, epoch);
+            rc2 = slab_launch(P, S->l_x[c], S->area, S->area, nullptr, inverse, sx);
+            if (rc2) return rc2;
+        }
+        if (S->Jp > 1) {
+            cudaEventRecord(S->ev_done, S->aux);
+            cudaStreamWaitEvent(st, S->ev_done, 0);
+        }
+        const int rc3 = slab_launch(P, S->l_z, S->area, out, nullptr, inverse, st);
+        if (rc3) return rc3;
+        if (S->timing) cudaEventRecord(S->ev_t[3], st);
+        return cudaGetLastError() == cudaSuccess ? FFTB200_SUCCESS : FFTB200_EXEC_FAILED;
+    }
     int rc = slab_launch(P, S->l_pass1, in, S->tmp, nullptr, inverse, st);
     if (rc) return rc;
     if (S->timing) cudaEventRecord(S->ev_t[1], st);

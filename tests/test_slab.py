@@ -109,6 +109,28 @@ def test_slab_fused_single_rank_chunks(fft, oracle, kind, chunks):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kind,planes", [("z2z", 4), ("c2c", 2), ("z2z", 8)])
+def test_slab_fused_single_rank_plane_chunks(fft, oracle, kind, planes, monkeypatch):
+    """complex transforms run y (+exchange) -> x -> z with the x pass pipelined over plane chunks"""
+    from regent_fft_arjun_b200 import distributed as D
+    monkeypatch.setenv("FFTB200_SLAB_PLANE_CHUNKS", str(planes))
+    dt = {"z2z": fft.complex64, "c2c": fft.complex32}[kind]
+    np_in = {"z2z": np.complex128, "c2c": np.complex64}[kind]
+    shape = (32, 64, 128)
+    x = oracle.synth(shape, np_in, seed=90)
+    plan = D.SlabFFT3D(shape, dt, rank=0, world=1, device="cuda:0", mode="p2p")
+    assert fft._lib.launch_count(plan.engine.h) == 1 + 2 * planes
+    xd = torch.from_numpy(x).cuda()
+    for _ in range(3):
+        plan.execute(xd)
+    torch.cuda.synchronize()
+    got = plan.gather_natural()
+    plan.destroy()
+    assert np.array_equal(xd.cpu().numpy(), x)
+    assert oracle.rel_l2(got, oracle.port_dft(x.astype(np.complex128))) <= oracle.tolerance(int(np.prod(shape)), kind == "c2c")
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["nccl", "p2p"])
 def test_slab_multi_gpu(built, mode):
     n = torch.cuda.device_count()
