@@ -321,8 +321,13 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> int:
     e_steps = max(4, min(steps, 8))
     if world == 1:
         npipe = 2
-        hx = [torch.empty(SHAPE, dtype=torch.complex128, pin_memory=True) for _ in range(npipe)]
-        hy = [torch.empty(SHAPE, dtype=torch.complex128, pin_memory=True) for _ in range(npipe)]
+        try:
+            hx = [torch.empty(SHAPE, dtype=torch.complex128, pin_memory=True) for _ in range(npipe)]
+            hy = [torch.empty(SHAPE, dtype=torch.complex128, pin_memory=True) for _ in range(npipe)]
+        except RuntimeError:  # not enough lockable host memory for 4 x 2 GiB: one transform in flight
+            npipe = 1
+            hx = [torch.empty(SHAPE, dtype=torch.complex128, pin_memory=True)]
+            hy = [torch.empty(SHAPE, dtype=torch.complex128, pin_memory=True)]
         for b in hx:
             b.copy_(x)
         pipes = [torch.cuda.Stream(device=dev) for _ in range(npipe)]
@@ -342,8 +347,8 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> int:
                 stream.wait_event(ev)
 
         h2d = d2h = N_TOTAL * ELT
-        e2e_path = ("fftb200_exec_z2z(host pinned in, host pinned out), 2 plans on 2 streams alternating: "
-                    "staged H2D, passes on HBM, D2H; consecutive steps' copies overlap")
+        e2e_path = ("fftb200_exec_z2z(host pinned in, host pinned out), %d plan(s) on %d stream(s) alternating: "
+                    "staged H2D, passes on HBM, D2H; consecutive steps' copies overlap" % (npipe, npipe))
     else:
         e2e_step, h2d, d2h = dplan.make_host_step(x)
 

@@ -3,6 +3,5 @@
 #define TT_IS_DOUBLE 1
 #define VAR V_CC
 #define COL_VARIANT 1
-#define ALT_ROWS 1
 #define TABLE_NAME tile_table_f64_cc
 #include "tile_inst.inc"
