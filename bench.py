@@ -176,6 +176,26 @@ def time_fftw(steps: int, warmup: int, budget_s: float, threads: int):
     return mean, reps, sample, kind, threads
 
 
+def time_fftw_faithful():
+    """What src/fft.rg's CPU branch really runs: the author's prebuilt scalar libfftw3.so (src/fft.rg:13), ESTIMATE,
+    ONE thread (fft.rg never calls fftw_init_threads).  512^3 takes ~14 s that way, so the sample is 256^3."""
+    import numpy as np
+    import oracle
+    try:
+        if not oracle.have_fftw("prebuilt"):
+            return {"value": None, "sample": "prebuilt libfftw3.so not present"}
+        F = oracle.FFTW.get("prebuilt")
+        n = 256
+        x = oracle.synth((n, n, n), np.complex128, seed=6)
+        times, _ = F.time_transform(x, real=False, threads=1, reps=2, warmup=0)
+        t = min(times)
+        fl = 5.0 * n ** 3 * math.log2(n ** 3)
+        return {"value": fl / t / 1e9, "unit": "GFLOP/s", "cores": 1, "ms_per_transform": t * 1e3,
+                "sample": "3D C2C fp64 256^3 (1/8 of the workload), reference's prebuilt scalar libfftw3.so.3.5.8, 1 thread, min of 2"}
+    except Exception as ex:
+        return {"value": None, "sample": f"failed: {ex}"}
+
+
 def run_reference(args, rank: int) -> int:
     if rank != 0:
         return 0
@@ -387,6 +407,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> int:
             mean_s, reps, sample, kind, used = time_fftw(3, 1, budget_s=25.0, threads=host_threads())
             cpu = {"value": FLOPS / mean_s / 1e9, "unit": "GFLOP/s", "cores": used, "kind": kind, "sample": sample,
                    "ms_per_transform": mean_s * 1e3}
+            cpu["reference_faithful_1thread"] = time_fftw_faithful()
         except Exception as ex:  # the baseline is a report, never a dependency of the product number
             cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
 

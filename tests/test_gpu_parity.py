@@ -650,3 +650,62 @@ def test_host_memory_regions_are_staged(L, oracle):
     got = hys.numpy()
     assert oracle.rel_l2(got, want) <= oracle.tolerance(128, False)
     assert np.array_equal(got == (-1 - 1j), want == (-1 - 1j))
+
+
+def test_random_plans_against_oracle(L, oracle):
+    """80 seeded random cufftPlanMany-style plans: rank 1-3, power-of-two and mixed-radix sizes, batches, padded
+    embeds and batch distances, all four types — against the oracle's fftw_plan_many_dft(_r2c) restatement;
+    padding must stay untouched and the input unchanged."""
+    rng = np.random.default_rng(20261018)
+    sizes_p2 = [2, 4, 8, 16, 32, 64, 128, 256]
+    sizes_any = [1, 3, 5, 6, 7, 9, 10, 12, 15, 20, 24, 30, 48, 96, 100]
+    for case in range(80):
+        kind = ["z2z", "c2c", "d2z", "r2c"][case % 4]
+        ftype, dt_in, dt_out = _kinds(L)[kind]
+        real, single = kind in ("d2z", "r2c"), kind in ("c2c", "r2c")
+        rank = int(rng.integers(1, 4))
+        pool = sizes_p2 if rng.random() < 0.6 else sizes_p2 + sizes_any
+        n = [int(rng.choice(pool)) for _ in range(rank)]
+        while int(np.prod(n)) > (1 << 18):
+            n[int(np.argmax(n))] //= 2
+        n = [max(1, v) for v in n]
+        if real and n[-1] < 2:
+            n[-1] = 2
+        batch = int(rng.integers(1, 5))
+        nout = n[:-1] + [n[-1] // 2 + 1] if real else list(n)
+        padded = rng.random() < 0.5
+        if padded:
+            ie = [n[0]] + [v + int(rng.integers(0, 4)) for v in n[1:]]
+            oe = [nout[0]] + [v + int(rng.integers(0, 4)) for v in nout[1:]]
+            if real and rng.random() < 0.5:
+                ie[-1] = max(ie[-1], 2 * oe[-1])            # the in-place-style padded real layout
+            idist = int(np.prod(ie)) + int(rng.integers(0, 6))
+            odist = int(np.prod(oe)) + int(rng.integers(0, 6))
+        else:
+            ie, oe = list(n), list(nout)
+            idist, odist = int(np.prod(ie)), int(np.prod(oe))
+        x = oracle.synth((batch * idist,), dt_in, 1000 + case)
+        fill = -3 - 4j
+        want = np.full(batch * odist, fill, dtype=np.complex128)
+        x64 = x.astype(np.float64 if real else np.complex128)
+        if real:
+            oracle.port_r2c_many(n, batch, x64, ie, 1, idist, want, oe, 1, odist)
+        else:
+            oracle.port_dft_many(n, batch, x64, ie, 1, idist, want, oe, 1, odist)
+        xd = torch.from_numpy(x).cuda()
+        yd = torch.full((batch * odist,), fill, dtype=_torch_dtype(dt_out), device="cuda")
+        if padded or batch > 1:
+            h = L.plan_many(rank, n, ie, 1, idist, oe, 1, odist, ftype, batch)
+        else:
+            h = L.plan_many(rank, n, None, 0, 0, None, 0, 0, ftype, 1)
+        L.execute(h, ftype, xd.data_ptr(), yd.data_ptr())
+        torch.cuda.synchronize()
+        L.destroy(h)
+        got = yd.cpu().numpy().astype(np.complex128)
+        touched = want != fill
+        tol = oracle.tolerance(int(np.prod(n)), single)
+        info = (case, kind, n, batch, ie, oe, idist, odist)
+        assert np.array_equal(got[~touched], want[~touched]), ("padding written", info)
+        if touched.any() and np.linalg.norm(want[touched]) > 0:
+            assert oracle.rel_l2(got[touched], want[touched]) <= tol, (oracle.rel_l2(got[touched], want[touched]), info)
+        assert np.array_equal(xd.cpu().numpy(), x), ("input modified", info)

@@ -1,3 +1,2 @@
 #!/bin/bash
-for alt in 0 1 2; do echo "== alt=$alt"; FFTB200_TILE_ALT=$alt python bench.py --no-cpu-baseline | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], [(p['kernel'][17:70],p['ms']) for p in d['roofline']['passes']])"; done
-python -c "import __graft_entry__ as g; g.smoke()"
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "random_plans or concurrent or host_memory" 2>&1 | tail -15
