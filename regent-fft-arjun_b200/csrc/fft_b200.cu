@@ -337,9 +337,10 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     ln.src = src;
     ln.dst = dst;
     TileParams &tp = ln.tp;
-    tp.tw = (L > ki->R) ? B.table(L / ki->cluster, L / ki->cluster, false) : nullptr;  // w_LL of the CTA-local stages
+    const int parts = ki->cluster * ki->split;  // CTAs that share one line
+    tp.tw = (L > ki->R) ? B.table(L / parts, L / parts, false) : nullptr;  // w_LL of the CTA-local stages
     tp.tw_aux = nullptr;
-    if (ki->cluster > 1) tp.tw_aux = B.table(L, L, false);  // cross-CTA stage twiddles w_L
+    if (parts > 1) tp.tw_aux = B.table(L, L, false);  // cross-CTA stage twiddles w_L
     if (variant == V_RR_R2C) tp.tw_aux = B.table(2ll * L, L / 2 + 1, false);
     tp.tw4_hi = tp.tw4_lo = nullptr;
     tp.tw4_shift = 0;
@@ -366,9 +367,14 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     tp.inverse = 0;
     const long long tiles = (long long)tp.tiles_per_outer * lv[1].n * lv[2].n;
     if (tiles <= 0 || tiles > 0x7fffffffll) return false;
-    if (tiles * ki->cluster > 0x7fffffffll) return false;
-    ln.grid = (unsigned)(tiles * ki->cluster);
+    if (tiles * parts > 0x7fffffffll) return false;
+    ln.grid = (unsigned)(tiles * parts);
     tp.n_tiles = (int)tiles;
+    {
+        // FFTB200_GRID_CAP=n (tuning): run single-CTA passes persistently on at most n CTAs
+        const int cap = env_int_or("FFTB200_GRID_CAP", 0);
+        if (cap > 0 && parts == 1 && ln.grid > (unsigned)cap) ln.grid = (unsigned)cap;
+    }
     tp.prefetch_tiles = 0;
     {
         // L2 prefetch of the tile that will run next in this CTA slot (distance = CTAs resident on the GPU).
@@ -385,7 +391,7 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P->device);
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)ki->fn, ki->threads, ki->smem_bytes) != cudaSuccess)
                 cudaGetLastError();
-            tp.prefetch_tiles = k * sms * (per_sm > 0 ? per_sm : 1);
+            tp.prefetch_tiles = k * sms * (per_sm > 0 ? per_sm : 1) / ki->split;
         }
     }
     const long long lines = lv[0].n * lv[1].n * lv[2].n;
@@ -395,9 +401,9 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     else
         ln.algo_bytes = (unsigned long long)lines * L * ce * 2ull;
     char buf[256];
-    snprintf(buf, sizeof buf, "tile %-11s %s L=%d R=%d W=%d threads=%d smem=%d cluster=%d lines=%lld tiles=%lld (%s)",
+    snprintf(buf, sizeof buf, "tile %-11s %s L=%d R=%d W=%d threads=%d smem=%d cluster=%d split=%d lines=%lld tiles=%lld (%s)",
              variant_name(variant), P->prec ? "fp64" : "fp32", L, ki->R, ki->W, ki->threads, ki->smem_bytes, ki->cluster,
-             lines, tiles, what);
+             ki->split, lines, tiles, what);
     ln.desc = buf;
     if (ki->smem_bytes > 48 * 1024) {
         if (cudaFuncSetAttribute((const void *)ki->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ki->smem_bytes) !=

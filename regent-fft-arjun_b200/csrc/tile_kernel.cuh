@@ -525,6 +525,81 @@ fft_fused_ab_kernel(const FusedParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Split pass for strided axes of L = 2*LL points without a cluster: the two CTAs of a tile each read the
+// WHOLE tile (both halves of every line: 2x the L2->SM traffic, but the second reader hits L2, so HBM traffic
+// stays 1x), form their half of the first radix-2 stage on the fly,
+//     y_c[j] = (x[j] + (-1)^c x[j+LL]) * w_L^(j*c),      c = CTA parity, j < LL,
+// and then run the ordinary length-LL pipeline and store rows c + 2k'.  No DSMEM, no cluster barrier: the two
+// CTAs are independent, which matters because these passes are bound by per-tile latency (measured on B200 at
+// 1024^3: cluster-of-2 kernel 11.3 ms per pass).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int LL, int CL, int R, int W, int VAR>
+__global__ void __launch_bounds__(TileTraits<T, LL, R, W, VAR>::THREADS, TileTraits<T, LL, R, W, VAR>::MIN_CTAS)
+fft_split_kernel(const TileParams p) {
+    using TR = TileTraits<T, LL, R, W, VAR>;
+    using C = cplx<T>;
+    static_assert(CL == 2, "split passes halve the line");
+    static_assert(!TR::LOAD_ROW && !TR::STORE_ROW && TR::S > 1, "split passes are column passes");
+    constexpr int LOG_W = TR::LOG_W;
+    constexpr int T_LINE = TR::T_LINE;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *sm = reinterpret_cast<C *>(smem_raw);
+    const int t = threadIdx.x;
+    const int w = t & (W - 1), u = t >> LOG_W;
+    const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);       // w_LL^k
+    const C *__restrict__ twL = reinterpret_cast<const C *>(p.tw_aux);  // w_L^k
+    const bool inv = p.inverse != 0;
+    const int work = p.n_tiles * CL;
+    for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
+        const int tile = wi / CL, c = wi - tile * CL;
+        const int o = tile / p.tiles_per_outer;
+        const int i0 = (tile - o * p.tiles_per_outer) * W;
+        const int o1 = o / p.n_o2, o2 = o - o1 * p.n_o2;
+        const C *__restrict__ gin = reinterpret_cast<const C *>(p.in) + o1 * p.in_os1 + o2 * p.in_os2;
+        // L2 prefetch of the tile this CTA slot runs next (issued by the c == 0 CTA for both halves)
+        if (p.prefetch_tiles > 0 && c == 0) {
+            const int ft = tile + p.prefetch_tiles;
+            if (ft < p.n_tiles) {
+                const int fo = ft / p.tiles_per_outer;
+                const int fi0 = (ft - fo * p.tiles_per_outer) * W;
+                const int fo1 = fo / p.n_o2, fo2 = fo - fo1 * p.n_o2;
+                if (fi0 + W <= p.n_inner) {
+                    const C *fin = reinterpret_cast<const C *>(p.in) + fo1 * p.in_os1 + fo2 * p.in_os2 + (long long)fi0 * p.in_is;
+                    constexpr int CH_ROW = (W * (int)sizeof(C) + 127) / 128;
+                    for (int ch = t; ch < CL * LL * CH_ROW; ch += TR::THREADS) {
+                        const int r = ch / CH_ROW, cc = ch - r * CH_ROW;
+                        const char *a = reinterpret_cast<const char *>(fin + (long long)r * p.in_ls) + cc * 128;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                    }
+                }
+            }
+        }
+        C v[R];
+        {
+            const bool ok = (i0 + w) < p.n_inner;
+            const C *src = gin + (long long)(i0 + w) * p.in_is + (long long)u * p.in_ls;
+#pragma unroll
+            for (int d = 0; d < R; ++d) {
+                C a = mk<T>((T)0, (T)0), b = mk<T>((T)0, (T)0);
+                if (ok) {
+                    a = ld_data<T>(src + (long long)(d * T_LINE) * p.in_ls);
+                    b = ld_data<T>(src + (long long)(LL + d * T_LINE) * p.in_ls);
+                }
+                if (inv) { T s = a.x; a.x = a.y; a.y = s; s = b.x; b.x = b.y; b.y = s; }
+                if (c == 0) {
+                    v[d] = cadd(a, b);
+                } else {
+                    v[d] = cmul(csub(a, b), ld_cplx<T>(twL + (u + d * T_LINE)));
+                }
+            }
+        }
+        tile_stages<T, LL, R, W, VAR>(v, sm, tw, w, u, w, u, w, u);
+        tile_store<T, LL, R, W, VAR>(v, p, o1, o2, i0, w, u, CL, c);
+        if (wi + (int)gridDim.x < work) __syncthreads();
+    }
+}
+
 // distributed shared memory through 32-bit shared::cluster addresses (cheaper in registers than
 // generic pointers from cluster.map_shared_rank)
 __device__ __forceinline__ unsigned dsmem_map(unsigned local_addr, unsigned cta_rank) {

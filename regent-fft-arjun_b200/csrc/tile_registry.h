@@ -8,6 +8,7 @@ struct TileKernelInfo {
     void (*fn)(const TileParams);
     int L, R, W, threads, smem_bytes;
     int cluster;  // CTAs per thread-block cluster (1 = ordinary launch); L = cluster * (length one CTA holds)
+    int split;    // independent CTAs per tile (fft_split_kernel; 1 otherwise); L = split * (length one CTA holds)
 };
 
 struct FusedKernelInfo {
