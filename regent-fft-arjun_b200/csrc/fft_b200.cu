@@ -91,6 +91,10 @@ static int env_int_or(const char *name, int dflt) {
 
 // one launch of a tile pass; cluster kernels go through cudaLaunchKernelEx with the cluster dimension
 static cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st, const TileParams &tp) {
+    if (tp.ticket) {
+        const cudaError_t e = cudaMemsetAsync(tp.ticket, 0, sizeof(unsigned), st);
+        if (e != cudaSuccess) return e;
+    }
     if (ki->cluster <= 1) {
         ki->fn<<<grid, ki->threads, ki->smem_bytes, st>>>(tp);
         return cudaGetLastError();
@@ -132,6 +136,7 @@ struct Launch {
     bool real_in = false;
     // common
     long long in_off = 0, out_off = 0;  // element offsets added to the source / destination base (chunked passes)
+    unsigned *ticket = nullptr;         // persistent (capped) launches: dynamic tile counter, zeroed before every launch
     int src = BUF_IN, dst = BUF_OUT;
     unsigned grid = 0;
     unsigned long long algo_bytes = 0;
@@ -373,8 +378,12 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     {
         // FFTB200_GRID_CAP=n (tuning): run single-CTA passes persistently on at most n CTAs
         const int cap = env_int_or("FFTB200_GRID_CAP", 0);
-        if (cap > 0 && parts == 1 && ln.grid > (unsigned)cap) ln.grid = (unsigned)cap;
+        if (cap > 0 && ki->cluster == 1 && ln.grid > (unsigned)cap) {
+            ln.grid = (unsigned)cap;
+            ln.ticket = (unsigned *)B.alloc(sizeof(unsigned));
+        }
     }
+    tp.ticket = nullptr;
     tp.prefetch_tiles = 0;
     {
         // L2 prefetch of the tile that will run next in this CTA slot (distance = CTAs resident on the GPU).
@@ -800,6 +809,7 @@ static int run_launches(Plan *P, const void *in, void *out, int inverse) {
             tp.in = src;
             tp.out = dst;
             tp.inverse = inverse;
+            tp.ticket = ln.ticket;
             ce = launch_tile(ln.ki, ln.grid, P->stream, tp);
         } else if (ln.kind == Launch::FUSED) {
             FusedParams fp;

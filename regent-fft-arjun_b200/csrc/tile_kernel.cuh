@@ -55,6 +55,7 @@ struct TileParams {
     long long in_ls, in_is, in_os1, in_os2;
     long long out_ls, out_is, out_os1, out_os2;
     int n_tiles;   // tiles of the whole pass (a CTA loops over tile = blockIdx.x + k * gridDim.x)
+    unsigned *ticket;    // != nullptr: persistent launch, tiles handed out by atomicAdd (zeroed before the launch)
     int prefetch_tiles;  // > 0: every CTA asks L2 to prefetch the input of tile + prefetch_tiles (the tile the
                          // CTA slot it occupies will run next), decoupling HBM latency from SM occupancy
     int n_inner;   // lines along the inner index
@@ -441,6 +442,26 @@ template <typename T, int L, int R, int W, int VAR>
 __global__ void __launch_bounds__(TileTraits<T, L, R, W, VAR>::THREADS, TileTraits<T, L, R, W, VAR>::MIN_CTAS)
 fft_tile_kernel(const TileParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (p.ticket != nullptr) {
+        // persistent launch with DYNAMIC tile assignment: SMs do not run at the same speed (two dies, near and far
+        // L2), so a static tile = blockIdx.x + k*gridDim.x split leaves the whole pass waiting for the slowest
+        // CTA (measured: 512^3 y axis 0.70 ms with one CTA per tile, 1.03 ms on 296 static persistent CTAs)
+        __shared__ int s_tile[2];
+        int cur = 0;
+        if (threadIdx.x == 0) s_tile[0] = (int)atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        for (;;) {
+            const int tile = s_tile[cur];
+            if (tile >= p.n_tiles) break;
+            unsigned next = 0;
+            if (threadIdx.x == 0) next = atomicAdd(p.ticket, 1u);  // consumed after the tile: latency hidden
+            fft_tile_body<T, L, R, W, VAR>(p, tile, smem_raw);
+            if (threadIdx.x == 0) s_tile[cur ^ 1] = (int)next;
+            __syncthreads();
+            cur ^= 1;
+        }
+        return;
+    }
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         fft_tile_body<T, L, R, W, VAR>(p, tile, smem_raw);
         if (TileTraits<T, L, R, W, VAR>::NEED_SMEM && tile + (int)gridDim.x < p.n_tiles) __syncthreads();
@@ -551,7 +572,16 @@ fft_split_kernel(const TileParams p) {
     const C *__restrict__ twL = reinterpret_cast<const C *>(p.tw_aux);  // w_L^k
     const bool inv = p.inverse != 0;
     const int work = p.n_tiles * CL;
-    for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
+    __shared__ int s_wi[2];
+    int cur = 0;
+    const bool dynamic = p.ticket != nullptr;
+    if (dynamic) {
+        if (t == 0) s_wi[0] = (int)atomicAdd(p.ticket, 1u);
+        __syncthreads();
+    }
+    for (int wi = dynamic ? s_wi[0] : (int)blockIdx.x; wi < work;) {
+        unsigned next = 0;
+        if (dynamic && t == 0) next = atomicAdd(p.ticket, 1u);
         const int tile = wi / CL, c = wi - tile * CL;
         const int o = tile / p.tiles_per_outer;
         const int i0 = (tile - o * p.tiles_per_outer) * W;
@@ -596,7 +626,15 @@ fft_split_kernel(const TileParams p) {
         }
         tile_stages<T, LL, R, W, VAR>(v, sm, tw, w, u, w, u, w, u);
         tile_store<T, LL, R, W, VAR>(v, p, o1, o2, i0, w, u, CL, c);
-        if (wi + (int)gridDim.x < work) __syncthreads();
+        if (dynamic) {
+            if (t == 0) s_wi[cur ^ 1] = (int)next;
+            __syncthreads();
+            cur ^= 1;
+            wi = s_wi[cur];
+        } else {
+            wi += (int)gridDim.x;
+            if (wi < work) __syncthreads();
+        }
     }
 }
 

@@ -17,7 +17,8 @@ dt = {"z2z": fft.complex64, "d2z": fft.double, "c2c": fft.complex32}[kind]
 flops = (2.5 if kind == "d2z" else 5.0) * n ** 3 * np.log2(float(n) ** 3)
 quick = len(sys.argv) > 3 and sys.argv[3] == "quick"
 one = len(sys.argv) > 3 and sys.argv[3] == "one"
-cfgs = [("p2p", 0, 148), ("p2p", 0, 296), ("p2p", 0, 0)] if one else [("p2p", 0, 148), ("p2p", 1, 0), ("p2p", 2, 0), ("nccl", 1, 0)] if quick else [("p2p", 1, 0)] + [("p2p", c, cap) for c in (2, 4, 8) for cap in (148, 296, 444, 0)] + [("nccl", 1, 0)]
+capmode = len(sys.argv) > 3 and sys.argv[3] == "cap"
+cfgs = [("p2p", 0, int(os.environ.get("FFTB200_SLAB_P2_CTAS", "148")))] if capmode else [("p2p", 0, 148), ("p2p", 0, 296), ("p2p", 0, 0)] if one else [("p2p", 0, 148), ("p2p", 1, 0), ("p2p", 2, 0), ("nccl", 1, 0)] if quick else [("p2p", 1, 0)] + [("p2p", c, cap) for c in (2, 4, 8) for cap in (148, 296, 444, 0)] + [("nccl", 1, 0)]
 for mode, chunks, cap in cfgs:
     os.environ["FFTB200_SLAB_P2_CTAS"] = str(cap)
     plan = D.SlabFFT3D(shape, dt, rank=rank, world=world, device=dev, mode=mode, chunks=chunks)
