@@ -19,6 +19,18 @@ template <typename T> using cplx = typename Vec2<T>::type;
 template <typename T> __device__ __forceinline__ cplx<T> mk(T x, T y) { cplx<T> r; r.x = x; r.y = y; return r; }
 template <typename C> __device__ __forceinline__ C cadd(C a, C b) { a.x += b.x; a.y += b.y; return a; }
 template <typename C> __device__ __forceinline__ C csub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
+// fp32 complex add/sub as ONE packed instruction (Blackwell FADD2: add.f32x2 / sub.f32x2 on a 64-bit register
+// pair).  The fp32 passes are bound by instruction issue, not by HBM, and adds are the bulk of a butterfly.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&r);
+}
 template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
     C r;
     r.x = a.x * b.x - a.y * b.y;
