@@ -378,7 +378,7 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     {
         // FFTB200_GRID_CAP=n (tuning): run single-CTA passes persistently on at most n CTAs
         const int cap = env_int_or("FFTB200_GRID_CAP", 0);
-        if (cap > 0 && ki->cluster == 1 && ln.grid > (unsigned)cap) {
+        if (cap > 0 && ki->cluster == 1 && variant == V_CC_PEER && ln.grid > (unsigned)cap) {
             ln.grid = (unsigned)cap;
             ln.ticket = (unsigned *)B.alloc(sizeof(unsigned));
         }

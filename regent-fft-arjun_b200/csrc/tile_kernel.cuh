@@ -442,6 +442,13 @@ template <typename T, int L, int R, int W, int VAR>
 __global__ void __launch_bounds__(TileTraits<T, L, R, W, VAR>::THREADS, TileTraits<T, L, R, W, VAR>::MIN_CTAS)
 fft_tile_kernel(const TileParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // Only the exchange passes of slab plans are ever launched with fewer CTAs than tiles.  Everything else runs
+    // exactly one tile per CTA and is compiled without the loop: keeping loop state alive across the body costs
+    // registers at the 64-register cap (measured: ~4 % on the 512^3 strided passes).
+    if constexpr (VAR != V_CC_PEER) {
+        fft_tile_body<T, L, R, W, VAR>(p, (int)blockIdx.x, smem_raw);
+        return;
+    }
     if (p.ticket != nullptr) {
         // persistent launch with DYNAMIC tile assignment: SMs do not run at the same speed (two dies, near and far
         // L2), so a static tile = blockIdx.x + k*gridDim.x split leaves the whole pass waiting for the slowest
