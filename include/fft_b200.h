@@ -65,7 +65,10 @@ typedef enum fftb200_type_e {
     FFTB200_R2C = 0x2a, /* float   -> complex32 */
     FFTB200_C2C = 0x29, /* complex32 -> complex32 */
     FFTB200_D2Z = 0x6a, /* double  -> complex64 */
-    FFTB200_Z2Z = 0x69  /* complex64 -> complex64 */
+    FFTB200_Z2Z = 0x69, /* complex64 -> complex64 */
+    /* inverse real transforms (no reference call site: src/fft.rg is forward-only) */
+    FFTB200_C2R = 0x2c, /* complex32 -> float  */
+    FFTB200_Z2D = 0x6c  /* complex64 -> double */
 } fftb200_type;
 
 typedef enum fftb200_result_e {
@@ -96,6 +99,11 @@ FFTB200_API int fftb200_exec_c2c(fftb200_handle plan, const void *in, void *out,
 FFTB200_API int fftb200_exec_z2z(fftb200_handle plan, const void *in, void *out, int direction);
 FFTB200_API int fftb200_exec_r2c(fftb200_handle plan, const void *in, void *out);
 FFTB200_API int fftb200_exec_d2z(fftb200_handle plan, const void *in, void *out);
+/* Unnormalised inverse of R2C / D2Z (cufftExecC2R / cufftExecZ2D, fftw_plan_dft_c2r semantics): in = packed half
+ * spectrum [..][n_last/2+1] complex, out = [..][n_last] reals = n_total * the original data.  The input is
+ * preserved (multi-dimensional plans go through a plan-owned work buffer).  Power-of-two sizes only. */
+FFTB200_API int fftb200_exec_c2r(fftb200_handle plan, const void *in, void *out);
+FFTB200_API int fftb200_exec_z2d(fftb200_handle plan, const void *in, void *out);
 
 /* Free the plan's device tables and work buffers.  Any thread; no current device needed. */
 FFTB200_API int fftb200_destroy(fftb200_handle plan);

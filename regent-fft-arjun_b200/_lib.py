@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("FFTB200_LIB_PATH") or os.path.join(_HERE, "libfft_b20
 
 # enums of include/fft_b200.h
 R2C, C2C, D2Z, Z2Z = 0x2A, 0x29, 0x6A, 0x69
+C2R, Z2D = 0x2C, 0x6C
 SUCCESS, INVALID_PLAN, ALLOC_FAILED, INVALID_TYPE, INVALID_VALUE = 0, 1, 2, 3, 4
 INTERNAL_ERROR, EXEC_FAILED, SETUP_FAILED, INVALID_SIZE, UNSUPPORTED = 5, 6, 7, 8, 16
 FORWARD, INVERSE = -1, 1
@@ -33,6 +34,8 @@ SYMBOLS = {
     "fftb200_exec_z2z": (ctypes.c_int, [_handle, _vp, _vp, ctypes.c_int]),
     "fftb200_exec_r2c": (ctypes.c_int, [_handle, _vp, _vp]),
     "fftb200_exec_d2z": (ctypes.c_int, [_handle, _vp, _vp]),
+    "fftb200_exec_c2r": (ctypes.c_int, [_handle, _vp, _vp]),
+    "fftb200_exec_z2d": (ctypes.c_int, [_handle, _vp, _vp]),
     "fftb200_destroy": (ctypes.c_int, [_handle]),
     "fftb200_get_work_size": (ctypes.c_int, [_handle, ctypes.POINTER(ctypes.c_ulonglong)]),
     "fftb200_get_launch_count": (ctypes.c_int, [_handle, _ip]),
@@ -113,6 +116,10 @@ def execute(h: int, ftype: int, in_ptr: int, out_ptr: int, direction: int = FORW
         rc = L.fftb200_exec_d2z(h, in_ptr, out_ptr)
     elif ftype == R2C:
         rc = L.fftb200_exec_r2c(h, in_ptr, out_ptr)
+    elif ftype == C2R:
+        rc = L.fftb200_exec_c2r(h, in_ptr, out_ptr)
+    elif ftype == Z2D:
+        rc = L.fftb200_exec_z2d(h, in_ptr, out_ptr)
     else:
         raise ValueError("bad transform type")
     check(rc, "fftb200_exec")

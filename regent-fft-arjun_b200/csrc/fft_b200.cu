@@ -36,8 +36,10 @@ namespace fftb200 {
 // ------------------------------------------------------------------------------------------
 typedef const TileKernelInfo *(*table_fn)(int *);
 static table_fn k_tables[2][V_COUNT] = {
-    {tile_table_f32_rr, tile_table_f32_cc, tile_table_f32_cctw, tile_table_f32_rc, tile_table_f32_r2c, tile_table_f32_ccp},
-    {tile_table_f64_rr, tile_table_f64_cc, tile_table_f64_cctw, tile_table_f64_rc, tile_table_f64_r2c, tile_table_f64_ccp}};
+    {tile_table_f32_rr, tile_table_f32_cc, tile_table_f32_cctw, tile_table_f32_rc, tile_table_f32_r2c, tile_table_f32_ccp,
+     tile_table_f32_c2r},
+    {tile_table_f64_rr, tile_table_f64_cc, tile_table_f64_cctw, tile_table_f64_rc, tile_table_f64_r2c, tile_table_f64_ccp,
+     tile_table_f64_c2r}};
 
 const TileKernelInfo *find_tile_kernel(int prec, int variant, int L) {
     int n = 0;
@@ -152,6 +154,7 @@ struct Plan {
     fftb200_type type = FFTB200_Z2Z;
     int prec = 1;       // 0 fp32, 1 fp64
     bool real = false;  // R2C / D2Z
+    bool c2r = false;   // C2R / Z2D (complex half spectrum in, reals out)
     bool generic = false;
     bool inplace_ok = false;  // in == out allowed
     std::vector<Launch> launches;
@@ -174,7 +177,7 @@ struct Plan {
     std::unique_ptr<Plan> fallback;
     std::mutex mu;
     size_t elt_in() const { return real ? (prec ? 8 : 4) : (prec ? 16 : 8); }
-    size_t elt_out() const { return prec ? 16 : 8; }
+    size_t elt_out() const { return c2r ? (prec ? 8 : 4) : (prec ? 16 : 8); }
 };
 
 struct DeviceGuard {
@@ -316,7 +319,7 @@ static void merge_levels(std::vector<Level> &lv) {
 }
 
 static const char *variant_name(int v) {
-    static const char *names[] = {"row", "col", "col+twiddle", "row->col", "r2c-row", "col->peers"};
+    static const char *names[] = {"row", "col", "col+twiddle", "row->col", "r2c-row", "col->peers", "c2r-row"};
     return names[v];
 }
 
@@ -329,8 +332,8 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     merge_levels(lv);
     if (lv.size() > 3) return false;
     while (lv.size() < 3) lv.push_back({1, 0, 0});
-    const bool load_row = (variant == V_RR || variant == V_RC || variant == V_RR_R2C);
-    const bool store_row = (variant == V_RR || variant == V_RR_R2C);
+    const bool load_row = (variant == V_RR || variant == V_RC || variant == V_RR_R2C || variant == V_RR_C2R);
+    const bool store_row = (variant == V_RR || variant == V_RR_R2C || variant == V_RR_C2R);
     if (load_row ? (in_ls != 1) : (lv[0].n > 1 && lv[0].is != 1)) return false;
     if (store_row ? (out_ls != 1) : (lv[0].n > 1 && lv[0].os != 1)) return false;
     if (lv[0].n > 0x7fffffffll || lv[1].n > 0x7fffffffll) return false;
@@ -347,6 +350,7 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     tp.tw_aux = nullptr;
     if (parts > 1) tp.tw_aux = B.table(L, L, false);  // cross-CTA stage twiddles w_L
     if (variant == V_RR_R2C) tp.tw_aux = B.table(2ll * L, L / 2 + 1, false);
+    if (variant == V_RR_C2R) tp.tw_aux = B.table(2ll * L, L, false);
     tp.tw4_hi = tp.tw4_lo = nullptr;
     tp.tw4_shift = 0;
     tp.tw4_mask = 0;
@@ -392,7 +396,7 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
         // 0.86 -> 1.12 ms) and contiguous-axis passes do not change, so only the first kind prefetches.
         // FFTB200_PREFETCH=0 switches it off, =k forces distance k on every single-CTA pass (tuning).
         const int forced = env_int_or("FFTB200_PREFETCH", -1);
-        const bool col_load = !(variant == V_RR || variant == V_RC || variant == V_RR_R2C);
+        const bool col_load = !load_row;
         const bool page_local = in_ls * (long long)(P->prec ? 16 : 8) <= 65536;
         const int k = forced >= 0 ? forced : ((col_load && page_local) ? 1 : 0);
         if (k > 0 && ki->cluster == 1) {
@@ -405,7 +409,7 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     }
     const long long lines = lv[0].n * lv[1].n * lv[2].n;
     const size_t ce = P->prec ? 16 : 8;
-    if (variant == V_RR_R2C)
+    if (variant == V_RR_R2C || variant == V_RR_C2R)
         ln.algo_bytes = (unsigned long long)lines * ((unsigned long long)L * ce + (unsigned long long)(L + 1) * ce);
     else
         ln.algo_bytes = (unsigned long long)lines * L * ce * 2ull;
@@ -631,6 +635,62 @@ static bool build_fast(Builder &B) {
 }
 
 // ------------------------------------------------------------------------------------------
+// inverse real plan (C2R / Z2D): backward COL passes over the n_last/2+1 columns (through a work buffer, so the
+// input survives), then the fused even/odd pre-pass + half-length backward FFT on the last axis
+// ------------------------------------------------------------------------------------------
+static bool build_c2r(Builder &B) {
+    Plan *P = B.P;
+    const int rank = P->rank, last = rank - 1;
+    const long long *n = P->n;
+    const int maxL = max_tile_length(P->prec);
+    for (int d = 0; d < rank; ++d)
+        if (!is_pow2(n[d])) return false;
+    if (P->in_stride[rank] != 1 || P->out_stride[rank] != 1) return false;
+    if (n[last] < 4 || n[last] / 2 > maxL) return false;
+    for (int d = 0; d < rank; ++d)
+        if (P->out_stride[d] & 1) return false;  // output rows / batches must start on a pair of reals
+    const long long nc = n[last] / 2 + 1;
+    long long outer_axes = 1;
+    for (int d = 0; d < last; ++d) {
+        if (n[d] > maxL) return false;
+        outer_axes *= n[d];
+    }
+    const size_t ce = P->prec ? 16 : 8;
+    int cur = BUF_IN;
+    long long cs[4];  // strides of the current complex array, [batch, d0.., d_last]
+    for (int d = 0; d <= rank; ++d) cs[d] = P->in_stride[d];
+    if (outer_axes > 1) {
+        long long ws[4];  // dense work layout [batch][n0]..[nc]
+        ws[rank] = 1;
+        for (int d = rank - 1; d >= 0; --d) ws[d] = ws[d + 1] * (d == last ? nc : n[d]);
+        const long long total = ws[0] * P->batch;
+        P->work_bytes = (size_t)total * ce;
+        P->work[0] = B.alloc(P->work_bytes);
+        if (!P->work[0]) return false;
+        for (int axis = last - 1; axis >= 0; --axis) {
+            if (n[axis] == 1) continue;
+            std::vector<Level> lv;
+            for (int d = rank - 1; d >= 0; --d) {
+                if (d == axis) continue;
+                lv.push_back({d == last ? nc : n[d], cs[d + 1], ws[d + 1]});
+            }
+            lv.push_back({(long long)P->batch, cs[0], ws[0]});
+            if (!add_tile_pass(B, V_CC, (int)n[axis], cs[axis + 1], ws[axis + 1], lv, cur, BUF_WORK0, 0, "strided axis (backward)"))
+                return false;
+            cur = BUF_WORK0;
+            for (int d = 0; d <= rank; ++d) cs[d] = ws[d];
+        }
+    }
+    // last axis: lines of nc complex -> n_last reals (addressed as n_last/2 complex pairs)
+    std::vector<Level> lv;
+    for (int d = last - 1; d >= 0; --d) lv.push_back({n[d], cs[d + 1], P->out_stride[d + 1] / 2});
+    lv.push_back({(long long)P->batch, cs[0], P->out_stride[0] / 2});
+    if (!add_tile_pass(B, V_RR_C2R, (int)(n[last] / 2), 1, 1, lv, cur, BUF_OUT, 0, "axis c2r")) return false;
+    P->inplace_ok = false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
 // generic plan
 // ------------------------------------------------------------------------------------------
 static unsigned grid_for(long long total) {
@@ -845,12 +905,16 @@ static int exec_plan(Plan *P, const void *in, void *out, int direction) {
     if (!in || !out) return FFTB200_INVALID_VALUE;
     if (direction != FFTB200_FORWARD && direction != FFTB200_INVERSE) return FFTB200_INVALID_VALUE;
     if (P->real && direction != FFTB200_FORWARD) return FFTB200_INVALID_VALUE;
+    if (P->c2r && direction != FFTB200_INVERSE) return FFTB200_INVALID_VALUE;
     if (in == out && !P->inplace_ok) return FFTB200_INVALID_VALUE;
     const bool host_in = is_host_memory(in), host_out = is_host_memory(out);
     if (!P->generic && !(host_in && host_out)) {
         const size_t a_in = P->real ? 2 * P->elt_in() : P->elt_in();
-        if ((!host_in && ((uintptr_t)in % a_in)) || (!host_out && ((uintptr_t)out % P->elt_out())))
+        const size_t a_out = P->c2r ? 2 * P->elt_out() : P->elt_out();
+        if ((!host_in && ((uintptr_t)in % a_in)) || (!host_out && ((uintptr_t)out % a_out))) {
+            if (P->c2r) return FFTB200_INVALID_VALUE;  // no generic path for inverse real transforms
             return exec_fallback(P, in, out, direction);
+        }
     }
     DeviceGuard g(P->device);
     std::lock_guard<std::mutex> lk(P->mu);
@@ -907,8 +971,9 @@ static int create_plan(Plan **out, int rank, const long long *n, int batch, cons
     std::unique_ptr<Plan> P(new Plan);
     if (cudaGetDevice(&P->device) != cudaSuccess) { cudaGetLastError(); return FFTB200_SETUP_FAILED; }
     P->type = type;
-    P->prec = (type == FFTB200_Z2Z || type == FFTB200_D2Z) ? 1 : 0;
+    P->prec = (type == FFTB200_Z2Z || type == FFTB200_D2Z || type == FFTB200_Z2D) ? 1 : 0;
     P->real = (type == FFTB200_R2C || type == FFTB200_D2Z);
+    P->c2r = (type == FFTB200_C2R || type == FFTB200_Z2D);
     P->rank = rank;
     P->batch = batch;
     for (int d = 0; d < rank; ++d) P->n[d] = n[d];
@@ -917,7 +982,8 @@ static int create_plan(Plan **out, int rank, const long long *n, int batch, cons
         long long li = 0, lo = 0, dense = 1;
         for (int d = 0; d < rank; ++d) {
             const long long no = (P->real && d == rank - 1) ? n[d] / 2 + 1 : n[d];
-            li += (n[d] - 1) * in_stride[d + 1];
+            const long long ni = (P->c2r && d == rank - 1) ? n[d] / 2 + 1 : n[d];
+            li += (ni - 1) * in_stride[d + 1];
             lo += (no - 1) * out_stride[d + 1];
             dense *= no;
         }
@@ -931,6 +997,14 @@ static int create_plan(Plan **out, int rank, const long long *n, int batch, cons
     Builder B;
     B.P = P.get();
     bool ok = false;
+    if (P->c2r) {
+        if (!build_c2r(B)) {
+            free_plan_resources(P.get());
+            return B.err != FFTB200_SUCCESS ? B.err : FFTB200_UNSUPPORTED;  // power-of-two, unit-stride layouts only
+        }
+        *out = P.release();
+        return FFTB200_SUCCESS;
+    }
     if (!force_generic) {
         ok = build_fast(B);
         if (!ok) {
@@ -969,9 +1043,11 @@ int fftb200_plan_many(fftb200_handle *plan, int rank, const int *n, const int *i
     if (!plan) return FFTB200_INVALID_VALUE;
     *plan = 0;
     if (!n || rank < 1 || rank > 3 || batch < 1) return FFTB200_INVALID_VALUE;
-    if (type != FFTB200_R2C && type != FFTB200_C2C && type != FFTB200_D2Z && type != FFTB200_Z2Z)
+    if (type != FFTB200_R2C && type != FFTB200_C2C && type != FFTB200_D2Z && type != FFTB200_Z2Z && type != FFTB200_C2R &&
+        type != FFTB200_Z2D)
         return FFTB200_INVALID_TYPE;
     const bool real = (type == FFTB200_R2C || type == FFTB200_D2Z);
+    const bool c2r = (type == FFTB200_C2R || type == FFTB200_Z2D);
     long long nn[3] = {1, 1, 1}, ie[3], oe[3];
     for (int d = 0; d < rank; ++d) {
         if (n[d] < 1) return FFTB200_INVALID_SIZE;
@@ -982,6 +1058,7 @@ int fftb200_plan_many(fftb200_handle *plan, int rank, const int *n, const int *i
         // cuFFT basic layout: packed, strides/dists ignored
         for (int d = 0; d < rank; ++d) { ie[d] = nn[d]; oe[d] = nn[d]; }
         if (real) oe[rank - 1] = nn[rank - 1] / 2 + 1;
+        if (c2r) ie[rank - 1] = nn[rank - 1] / 2 + 1;
         id = od = 1;
         for (int d = 0; d < rank; ++d) { id *= ie[d]; od *= oe[d]; }
     } else {
@@ -990,7 +1067,8 @@ int fftb200_plan_many(fftb200_handle *plan, int rank, const int *n, const int *i
             ie[d] = inembed[d];
             oe[d] = onembed[d];
             const long long need_o = (real && d == rank - 1) ? nn[d] / 2 + 1 : nn[d];
-            if (d > 0 && (ie[d] < nn[d] || oe[d] < need_o)) return FFTB200_INVALID_VALUE;
+            const long long need_i = (c2r && d == rank - 1) ? nn[d] / 2 + 1 : nn[d];
+            if (d > 0 && (ie[d] < need_i || oe[d] < need_o)) return FFTB200_INVALID_VALUE;
         }
         is = istride; os = ostride; id = idist; od = odist;
         if (batch > 1 && (id < 1 || od < 1)) return FFTB200_INVALID_VALUE;
@@ -1038,6 +1116,12 @@ int fftb200_exec_r2c(fftb200_handle plan, const void *in, void *out) {
 }
 int fftb200_exec_d2z(fftb200_handle plan, const void *in, void *out) {
     return exec_typed(plan, in, out, FFTB200_FORWARD, FFTB200_D2Z);
+}
+int fftb200_exec_c2r(fftb200_handle plan, const void *in, void *out) {
+    return exec_typed(plan, in, out, FFTB200_INVERSE, FFTB200_C2R);
+}
+int fftb200_exec_z2d(fftb200_handle plan, const void *in, void *out) {
+    return exec_typed(plan, in, out, FFTB200_INVERSE, FFTB200_Z2D);
 }
 
 int fftb200_destroy(fftb200_handle plan) {

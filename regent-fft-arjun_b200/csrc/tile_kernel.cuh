@@ -40,7 +40,9 @@ enum TileVariant : int {
     V_CC_PEER = 5, // COL/COL, output index k scattered over up to 16 destination buffers: the slab
                    // exchange fused into the FFT pass (peer GPUs' memory over NVLink, or the blocks of
                    // a local all-to-all send buffer)
-    V_COUNT = 6
+    V_RR_C2R = 6,  // ROW load of L+1 half-spectrum bins, even/odd pre-pass, half-length inverse FFT, ROW store of
+                   // 2L reals (the inverse of V_RR_R2C; no reference call site: src/fft.rg is forward-only)
+    V_COUNT = 7
 };
 
 constexpr int MAX_PEERS = 16;
@@ -49,7 +51,7 @@ struct TileParams {
     const void *in;
     void *out;
     const void *tw;      // w_L^k, k in [0,L), forward sign, complex<T>
-    const void *tw_aux;  // V_RR_R2C: w_{2L}^k, k in [0, L/2], complex<T>
+    const void *tw_aux;  // V_RR_R2C: w_{2L}^k, k in [0, L/2]; V_RR_C2R: k in [0, L); cluster/split: w_L^k; complex<T>
     const double2 *tw4_hi;  // V_CC_TW: w_N^(m) = hi[m >> tw4_shift] * lo[m & tw4_mask]
     const double2 *tw4_lo;
     long long in_ls, in_is, in_os1, in_os2;
@@ -79,9 +81,9 @@ template <typename T, int L_, int R_, int W_, int VAR_> struct TileTraits {
     static constexpr int T_LINE = L / R;                            // threads per line
     static constexpr int LOG_TL = ilog2c(T_LINE);
     static constexpr int THREADS = T_LINE * W;
-    static constexpr bool LOAD_ROW = (VAR == V_RR || VAR == V_RC || VAR == V_RR_R2C);
-    static constexpr bool STORE_ROW = (VAR == V_RR || VAR == V_RR_R2C);
-    static constexpr bool NEED_SMEM = (S > 1) || (VAR == V_RR_R2C);
+    static constexpr bool LOAD_ROW = (VAR == V_RR || VAR == V_RC || VAR == V_RR_R2C || VAR == V_RR_C2R);
+    static constexpr bool STORE_ROW = (VAR == V_RR || VAR == V_RR_R2C || VAR == V_RR_C2R);
+    static constexpr bool NEED_SMEM = (S > 1) || (VAR == V_RR_R2C) || (VAR == V_RR_C2R);
     static constexpr int SMEM_BYTES = NEED_SMEM ? L * W * (int)sizeof(cplx<T>) : 0;
     // swizzle group width: 8 x 16 B or 16 x 8 B = 128 B = all 32 banks.  Pure column passes need no
     // swizzle at all: their lanes run along w first, so every quarter-warp (16-byte elements) or
@@ -380,9 +382,43 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
                 if constexpr (DATA_CG) x = __ldcg(src + (long long)(d * T_LINE) * p.in_ls);
                 else x = ld_data<T>(src + (long long)(d * T_LINE) * p.in_ls);
             }
-            if (inv) { T s = x.x; x.x = x.y; x.y = s; }
+            if (inv && VAR != V_RR_C2R) { T s = x.x; x.x = x.y; x.y = s; }
             v[d] = x;
         }
+    }
+
+    if constexpr (VAR == V_RR_C2R) {
+        // ---- even/odd pre-pass: from the half spectrum X[0..L] of 2L reals build
+        //   Z'[k] = (X[k] + conj X[L-k]) + i * conj(w_{2L}^k) * (X[k] - conj X[L-k])      ( = 2 Z[k] )
+        // whose unnormalised inverse transform z has x[2j] = Re z[j], x[2j+1] = Im z[j]  (the launch always
+        // runs with the re/im swap on, i.e. as a backward transform).
+        const bool ok = (i0 + w1) < p.n_inner;
+        T xl_re = (T)0;  // Re X[L], needed for k = 0 only
+        if (u1 == 0 && ok) xl_re = ld_cplx<T>(gin + (long long)(i0 + w1) * p.in_is + (long long)L * p.in_ls).x;
+#pragma unroll
+        for (int d = 0; d < R; ++d) {
+            const int idx = ((u1 + d * T_LINE) << LOG_W) | w1;
+            sm[idx ^ swz_fold<SB, IDX_BITS>(idx)] = v[d];
+        }
+        __syncthreads();
+        const C *tw2 = reinterpret_cast<const C *>(p.tw_aux);
+#pragma unroll
+        for (int d = 0; d < R; ++d) {
+            const int k = u1 + d * T_LINE;
+            C zp;
+            if (k == 0) {
+                zp = mk<T>(v[d].x + xl_re, v[d].x - xl_re);
+            } else {
+                const int ib = ((L - k) << LOG_W) | w1;
+                const C a = v[d];
+                const C b = cconj(sm[ib ^ swz_fold<SB, IDX_BITS>(ib)]);
+                const C sum = cadd(a, b);
+                const C tt = cmul(csub(a, b), cconj(ld_cplx<T>(tw2 + k)));
+                zp = mk<T>(sum.x - tt.y, sum.y + tt.x);
+            }
+            v[d] = mk<T>(zp.y, zp.x);  // swap: backward transform through the forward butterflies
+        }
+        __syncthreads();  // every partner has been read before the stages overwrite shared memory
     }
 
     const int wl = TR::STORE_ROW ? w_row : w_col;

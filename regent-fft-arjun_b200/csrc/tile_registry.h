@@ -32,11 +32,13 @@ FFTB200_DECL_TABLE(tile_table_f64_cctw);
 FFTB200_DECL_TABLE(tile_table_f64_rc);
 FFTB200_DECL_TABLE(tile_table_f64_r2c);
 FFTB200_DECL_TABLE(tile_table_f64_ccp);
+FFTB200_DECL_TABLE(tile_table_f64_c2r);
 FFTB200_DECL_TABLE(tile_table_f32_rr);
 FFTB200_DECL_TABLE(tile_table_f32_cc);
 FFTB200_DECL_TABLE(tile_table_f32_cctw);
 FFTB200_DECL_TABLE(tile_table_f32_rc);
 FFTB200_DECL_TABLE(tile_table_f32_r2c);
 FFTB200_DECL_TABLE(tile_table_f32_ccp);
+FFTB200_DECL_TABLE(tile_table_f32_c2r);
 
 }  // namespace fftb200

@@ -718,3 +718,56 @@ def test_random_plans_against_oracle(L, oracle):
         if touched.any() and np.linalg.norm(want[touched]) > 0:
             assert oracle.rel_l2(got[touched], want[touched]) <= tol, (oracle.rel_l2(got[touched], want[touched]), info)
         assert np.array_equal(xd.cpu().numpy(), x), ("input modified", info)
+
+
+def test_inverse_real_transforms(L, oracle):
+    """C2R / Z2D (no reference call site): unnormalised inverse of the R2C / D2Z results,
+    against numpy's irfftn of the oracle's half spectrum and as a GPU round trip; the input is preserved."""
+    cases = [("z2d", (8,)), ("z2d", (4096,)), ("z2d", (16384,)), ("z2d", (64, 128)), ("z2d", (16, 32, 64)), ("z2d", (4, 4, 4)),
+             ("c2r", (1024,)), ("c2r", (32768,)), ("c2r", (256, 64)), ("c2r", (8, 16, 128)), ("z2d", (2, 1024, 8)),
+             ("z2d", (1024, 64)), ("c2r", (2048, 32))]
+    for i, (kind, shape) in enumerate(cases):
+        single = kind == "c2r"
+        rdt, cdt = (np.float32, np.complex64) if single else (np.float64, np.complex128)
+        ftype, fwd = (L.C2R, L.R2C) if single else (L.Z2D, L.D2Z)
+        x = oracle.synth(shape, rdt, 1200 + i)
+        X = oracle.port_r2c(x.astype(np.float64)).astype(cdt)           # half spectrum [.., n/2+1]
+        n_total = int(np.prod(shape))
+        Xd = torch.from_numpy(X).cuda()
+        yd = torch.zeros(shape, dtype=_torch_dtype(rdt), device="cuda")
+        h = L.plan_many(len(shape), list(shape), None, 0, 0, None, 0, 0, ftype, 1)
+        L.execute(h, ftype, Xd.data_ptr(), yd.data_ptr())
+        torch.cuda.synchronize()
+        desc = L.describe(h)
+        L.destroy(h)
+        assert "c2r-row" in desc and "generic" not in desc
+        want = np.fft.irfftn(X.astype(np.complex128), s=shape, axes=tuple(range(len(shape)))) * n_total
+        tol = oracle.tolerance(n_total, single)
+        assert oracle.rel_l2(yd.cpu().numpy(), want) <= tol, (kind, shape, oracle.rel_l2(yd.cpu().numpy(), want))
+        assert np.array_equal(Xd.cpu().numpy(), X), "c2r input modified"
+        # round trip on the GPU: C2R(R2C(x)) = N x
+        xd = torch.from_numpy(x).cuda()
+        Zd = torch.zeros(X.shape, dtype=_torch_dtype(cdt), device="cuda")
+        hf = L.plan_many(len(shape), list(shape), None, 0, 0, None, 0, 0, fwd, 1)
+        L.execute(hf, fwd, xd.data_ptr(), Zd.data_ptr())
+        hb = L.plan_many(len(shape), list(shape), None, 0, 0, None, 0, 0, ftype, 1)
+        L.execute(hb, ftype, Zd.data_ptr(), yd.data_ptr())
+        torch.cuda.synchronize()
+        L.destroy(hf)
+        L.destroy(hb)
+        assert oracle.rel_l2(yd.cpu().numpy() / n_total, x.astype(np.float64)) <= 2 * tol, (kind, shape, "round trip")
+    # batched + error conventions
+    h = L.plan_many(1, [256], None, 0, 0, None, 0, 0, L.Z2D, 3)
+    x = oracle.synth((3, 256), np.float64, 1300)
+    X = np.stack([oracle.port_r2c(r) for r in x])
+    Xd = torch.from_numpy(X).cuda()
+    yd = torch.zeros((3, 256), dtype=torch.float64, device="cuda")
+    L.execute(h, L.Z2D, Xd.data_ptr(), yd.data_ptr())
+    torch.cuda.synchronize()
+    assert oracle.rel_l2(yd.cpu().numpy() / 256, x) <= 2 * oracle.tolerance(256, False)
+    lib = L.lib()
+    assert lib.fftb200_exec_d2z(h, Xd.data_ptr(), yd.data_ptr()) == L.INVALID_TYPE
+    L.destroy(h)
+    hbad = ctypes.c_ulonglong(0)
+    n3 = (ctypes.c_int * 1)(12)
+    assert lib.fftb200_plan_many(ctypes.byref(hbad), 1, n3, None, 0, 0, None, 0, 0, L.Z2D, 1) == L.UNSUPPORTED   # not 2^k

@@ -1,2 +1,2 @@
 #!/bin/bash
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "inverse_real or golden or random or properties" 2>&1 | tail -15
