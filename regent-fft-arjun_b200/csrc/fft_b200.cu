@@ -253,7 +253,7 @@ static Plan *unregister_plan(fftb200_handle h) {
 struct Builder {
     Plan *P;
     int err = FFTB200_SUCCESS;
-    std::map<std::pair<int, long long>, void *> cache;  // (kind, n) -> device table
+    std::map<std::pair<std::pair<int, long long>, long long>, void *> cache;  // ((kind, n), count) -> device table
 
     void *upload(const void *host, size_t bytes) {
         void *d = nullptr;
@@ -266,7 +266,7 @@ struct Builder {
     // w_n^k for k in [0, count), in the plan's precision (kind 0) or always fp64 (kind 1)
     void *table(long long n, long long count, bool force_double, long long step = 1) {
         const int kind = (force_double ? 1 : 0) + (step != 1 ? 2 : 0);
-        auto key = std::make_pair(kind * 4 + (count == n ? 0 : 1), n * 64 + (step % 64));
+        auto key = std::make_pair(std::make_pair(kind, n), count);
         if (step == 1) {
             auto it = cache.find(key);
             if (it != cache.end()) return it->second;

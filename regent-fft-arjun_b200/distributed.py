@@ -119,7 +119,20 @@ class SlabFFT3D:
             self.send = torch.empty(self.blocks_shape, dtype=self.dtype_out.torch, device=self.device)
             self.recv = torch.empty(self.blocks_shape, dtype=self.dtype_out.torch, device=self.device)
         if mode == "p2p" and engine is None and self.world > 1:
-            self.engine.connect(group)
+            # mapping the peers' exchange areas can fail on one rank only (IPC disabled, no P2P path): agree on
+            # the outcome collectively, otherwise the ranks that succeeded would wait for flags that never come
+            ok = 1
+            try:
+                self.engine.connect(group)
+            except _lib.FFTB200Error as ex:
+                ok = 0
+                self.connect_error = str(ex)
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                self.mode = "nccl"       # staged exchange through all_to_all_single; still the CUDA library's passes
+                self.send = torch.empty(self.blocks_shape, dtype=self.dtype_out.torch, device=self.device)
+                self.recv = torch.empty(self.blocks_shape, dtype=self.dtype_out.torch, device=self.device)
         n0, n1, n2 = self.shape
         n2c = self.local_out_shape[2]
         ce = self.dtype_out.size
@@ -197,5 +210,10 @@ class SlabFFT3D:
         return assemble_transposed([p.cpu().numpy() for p in parts])
 
     def destroy(self):
+        """collective: no rank frees its exchange area while a peer may still store into it"""
+        if self.world > 1 and dist.is_initialized():
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
         if hasattr(self.engine, "destroy"):
             self.engine.destroy()
