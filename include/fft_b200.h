@@ -143,6 +143,9 @@ FFTB200_API int fftb200_get_launch_ms(fftb200_handle plan, int i, float *ms);
  *      all-to-all (e.g. NCCL) into `recv`; exec_post finishes from `recv`. */
 FFTB200_API int fftb200_slab_plan(fftb200_handle *plan, const int *n /* [3] */, fftb200_type type, int rank, int nranks,
                                   int chunks);
+/* 2-D slabs (C2C / Z2Z): rank r holds in [n0/G][n1] and receives out [n1/G][n0] (transposed-out); the row FFT's
+ * store is the global transpose.  Fused exchange only (connect as above, then fftb200_slab_exec). */
+FFTB200_API int fftb200_slab_plan_2d(fftb200_handle *plan, const int *n /* [2] */, fftb200_type type, int rank, int nranks);
 FFTB200_API int fftb200_slab_get_ipc_handle(fftb200_handle plan, void *handle64);
 FFTB200_API int fftb200_slab_connect_ipc(fftb200_handle plan, const void *handles /* nranks x 64 bytes, rank order */);
 FFTB200_API int fftb200_slab_get_area(fftb200_handle plan, void **area, unsigned long long *bytes);

@@ -44,6 +44,7 @@ SYMBOLS = {
     "fftb200_set_profiling": (ctypes.c_int, [_handle, ctypes.c_int]),
     "fftb200_get_launch_ms": (ctypes.c_int, [_handle, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
     "fftb200_slab_plan": (ctypes.c_int, [ctypes.POINTER(_handle), _ip, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "fftb200_slab_plan_2d": (ctypes.c_int, [ctypes.POINTER(_handle), _ip, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "fftb200_slab_get_ipc_handle": (ctypes.c_int, [_handle, _vp]),
     "fftb200_slab_connect_ipc": (ctypes.c_int, [_handle, _vp]),
     "fftb200_slab_get_area": (ctypes.c_int, [_handle, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_ulonglong)]),
@@ -167,6 +168,12 @@ def launch_ms(h: int, i: int) -> float:
 def slab_plan(n, ftype, rank, nranks, chunks=1) -> int:
     h = _handle(0)
     check(lib().fftb200_slab_plan(ctypes.byref(h), _ints(n), ftype, rank, nranks, chunks), "fftb200_slab_plan")
+    return int(h.value)
+
+
+def slab_plan_2d(n, ftype, rank, nranks) -> int:
+    h = _handle(0)
+    check(lib().fftb200_slab_plan_2d(ctypes.byref(h), _ints(n), ftype, rank, nranks), "fftb200_slab_plan_2d")
     return int(h.value)
 
 

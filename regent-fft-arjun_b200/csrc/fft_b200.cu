@@ -37,9 +37,9 @@ namespace fftb200 {
 typedef const TileKernelInfo *(*table_fn)(int *);
 static table_fn k_tables[2][V_COUNT] = {
     {tile_table_f32_rr, tile_table_f32_cc, tile_table_f32_cctw, tile_table_f32_rc, tile_table_f32_r2c, tile_table_f32_ccp,
-     tile_table_f32_c2r},
+     tile_table_f32_c2r, tile_table_f32_rcp},
     {tile_table_f64_rr, tile_table_f64_cc, tile_table_f64_cctw, tile_table_f64_rc, tile_table_f64_r2c, tile_table_f64_ccp,
-     tile_table_f64_c2r}};
+     tile_table_f64_c2r, tile_table_f64_rcp}};
 
 const TileKernelInfo *find_tile_kernel(int prec, int variant, int L) {
     int n = 0;
@@ -319,7 +319,7 @@ static void merge_levels(std::vector<Level> &lv) {
 }
 
 static const char *variant_name(int v) {
-    static const char *names[] = {"row", "col", "col+twiddle", "row->col", "r2c-row", "col->peers", "c2r-row"};
+    static const char *names[] = {"row", "col", "col+twiddle", "row->col", "r2c-row", "col->peers", "c2r-row", "row->peers"};
     return names[v];
 }
 
@@ -332,7 +332,8 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
     merge_levels(lv);
     if (lv.size() > 3) return false;
     while (lv.size() < 3) lv.push_back({1, 0, 0});
-    const bool load_row = (variant == V_RR || variant == V_RC || variant == V_RR_R2C || variant == V_RR_C2R);
+    const bool load_row =
+        (variant == V_RR || variant == V_RC || variant == V_RR_R2C || variant == V_RR_C2R || variant == V_RC_PEER);
     const bool store_row = (variant == V_RR || variant == V_RR_R2C || variant == V_RR_C2R);
     if (load_row ? (in_ls != 1) : (lv[0].n > 1 && lv[0].is != 1)) return false;
     if (store_row ? (out_ls != 1) : (lv[0].n > 1 && lv[0].os != 1)) return false;
@@ -1147,6 +1148,7 @@ int fftb200_get_launch_count(fftb200_handle plan, int *launches) {
     if (P->slab) {  // kernels one fused slab exec issues: pass 1, J x (pass 2 + pass 3), hand-shake kernels
         const int J = P->real ? P->slab->J : P->slab->Jp;
         *launches = 1 + 2 * J + (P->slab->G > 1 ? 2 + 2 * J : 0);
+        if (P->slab->two_d) *launches = 2 + (P->slab->G > 1 ? 4 : 0);
     }
     return FFTB200_SUCCESS;
 }
@@ -1216,6 +1218,18 @@ int fftb200_slab_plan(fftb200_handle *plan, const int *n, fftb200_type type, int
         return FFTB200_INVALID_TYPE;
     Plan *P = nullptr;
     const int rc = slab_create(&P, n, type, rank, nranks, chunks);
+    if (rc != FFTB200_SUCCESS) return rc;
+    *plan = register_plan(P);
+    return FFTB200_SUCCESS;
+}
+
+int fftb200_slab_plan_2d(fftb200_handle *plan, const int *n, fftb200_type type, int rank, int nranks) {
+    if (!plan) return FFTB200_INVALID_VALUE;
+    *plan = 0;
+    if (!n) return FFTB200_INVALID_VALUE;
+    if (type != FFTB200_C2C && type != FFTB200_Z2Z) return FFTB200_INVALID_TYPE;
+    Plan *P = nullptr;
+    const int rc = slab_create_2d(&P, n, type, rank, nranks);
     if (rc != FFTB200_SUCCESS) return rc;
     *plan = register_plan(P);
     return FFTB200_SUCCESS;
@@ -1299,6 +1313,7 @@ int fftb200_slab_exec_pre(fftb200_handle plan, const void *in, void *send, int d
     if (!in || !send) return FFTB200_INVALID_VALUE;
     int inverse = 0;
     const int rc = slab_direction(P, direction, &inverse);
+    if (P->slab->two_d) return FFTB200_UNSUPPORTED;  // 2-D slabs run the fused exchange only
     return rc ? rc : slab_exec_pre(P, in, send, inverse);
 }
 
@@ -1308,6 +1323,7 @@ int fftb200_slab_exec_post(fftb200_handle plan, const void *recv, void *out, int
     if (!recv || !out) return FFTB200_INVALID_VALUE;
     int inverse = 0;
     const int rc = slab_direction(P, direction, &inverse);
+    if (P->slab->two_d) return FFTB200_UNSUPPORTED;
     return rc ? rc : slab_exec_post(P, recv, out, inverse);
 }
 

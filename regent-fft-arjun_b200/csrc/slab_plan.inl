@@ -49,6 +49,10 @@ struct SlabState {
     int Jp = 0;
     std::vector<int> l_y, l_x;
     int l_z = -1;
+    // 2-D slabs: rank r holds in [n0/G][n1], gets out [n1/G][n0] (transposed-out): row FFT whose store is the
+    // global transpose into the peers' receive slabs, hand-shake, row FFT over the received (now contiguous) n0
+    bool two_d = false;
+    int l_2a = -1, l_2b = -1;
 };
 
 // flags: [kind 0 = "receive buffer free", 1.. = "chunk j written"][source rank] epochs
@@ -304,6 +308,69 @@ static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, in
     return FFTB200_SUCCESS;
 }
 
+static int slab_create_2d(Plan **out, const int *n, fftb200_type type, int rank, int G) {
+    if (G < 1 || G > MAX_PEERS || rank < 0 || rank >= G) return FFTB200_INVALID_VALUE;
+    for (int d = 0; d < 2; ++d)
+        if (n[d] < 2 || !is_pow2(n[d])) return FFTB200_INVALID_SIZE;
+    if (!is_pow2(G) || n[0] % G || n[1] % G) return FFTB200_INVALID_SIZE;
+    std::unique_ptr<Plan> P(new Plan);
+    if (cudaGetDevice(&P->device) != cudaSuccess) { cudaGetLastError(); return FFTB200_SETUP_FAILED; }
+    P->type = type;
+    P->prec = (type == FFTB200_Z2Z) ? 1 : 0;
+    P->rank = 2;
+    P->batch = 1;
+    const int maxL = max_tile_length(P->prec);
+    if (n[0] > maxL || n[1] > maxL) return FFTB200_INVALID_SIZE;
+    SlabState *S = new SlabState;
+    P->slab = S;
+    S->two_d = true;
+    S->rank = rank;
+    S->G = G;
+    S->J = S->Jp = 1;
+    S->n0 = n[0]; S->n1 = n[1]; S->n2 = S->n2c = 1;
+    S->n0l = n[0] / G;
+    S->n1l = n[1] / G;
+    const long long per_line = P->prec ? 8 : 16;
+    const long long n0p = (S->n0 + per_line - 1) / per_line * per_line;  // receive-slab row pitch, whole 128-byte lines
+    S->n2p = n0p;
+    P->n[0] = S->n0l; P->n[1] = n[1];
+    const size_t ce = P->prec ? 16 : 8;
+    Builder B;
+    B.P = P.get();
+    auto fail = [&](int code) {
+        free_plan_resources(P.get());
+        return code;
+    };
+    S->recv_bytes = (size_t)(S->n1l * n0p) * ce;
+    S->flags_off = (S->recv_bytes + 255) / 256 * 256;
+    S->area_bytes = S->flags_off + sizeof(unsigned long long) * MAX_PEERS * 64;
+    if (cudaMalloc(&S->area, S->area_bytes) != cudaSuccess) { cudaGetLastError(); return fail(FFTB200_ALLOC_FAILED); }
+    if (cudaMemset((char *)S->area + S->flags_off, 0, S->area_bytes - S->flags_off) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
+    P->work_bytes = S->recv_bytes;
+    {   // pass A: rows of n1 (contiguous) -> column k of the transpose lives on rank k / n1l
+        std::vector<Level> lv = {{S->n0l, S->n1, 1}};
+        if (!add_tile_pass(B, V_RC_PEER, (int)S->n1, 1, n0p, lv, BUF_IN, BUF_OUT, 0, "2-D slab: row FFT, store = global transpose (peer memory)"))
+            return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
+        Launch &ln = P->launches.back();
+        ln.out_off = (long long)rank * S->n0l;
+        ln.tp.peer_shift = ilog2ll(S->n1l);
+        ln.tp.peer_mask = (int)S->n1l - 1;
+        S->l_2a = (int)P->launches.size() - 1;
+    }
+    {   // pass B: the received slab [n1l][n0p] holds whole columns: row FFT over n0 -> out [n1l][n0]
+        std::vector<Level> lv = {{S->n1l, n0p, S->n0}};
+        if (!add_tile_pass(B, V_RR, (int)S->n0, 1, 1, lv, BUF_WORK1, BUF_OUT, 0, "2-D slab: column FFT on the received slab"))
+            return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
+        S->l_2b = (int)P->launches.size() - 1;
+    }
+    for (int i = 0; i < 5; ++i)
+        if (cudaEventCreate(&S->ev_t[i]) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
+    S->peer_area[rank] = S->area;
+    if (G == 1) S->connected = true;
+    *out = P.release();
+    return FFTB200_SUCCESS;
+}
+
 static unsigned long long *slab_flags(SlabState *S, int d) {
     return (unsigned long long *)((char *)S->peer_area[d] + S->flags_off);
 }
@@ -325,6 +392,21 @@ static int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
     if (S->timing) cudaEventRecord(S->ev_t[0], st);
     // my receive buffer is free again (stream order: after my previous transform's pass 3)
     if (S->G > 1) slab_signal_kernel<<<1, 32, 0, st>>>(peers, S->G, S->rank, 0, epoch);
+    if (S->two_d) {
+        if (S->G > 1) slab_wait_kernel<<<1, 32, 0, st>>>(slab_flags(S, S->rank), S->G, 0, epoch);
+        if (S->timing) cudaEventRecord(S->ev_t[1], st);
+        int rc2 = slab_launch(P, S->l_2a, in, nullptr, recv, inverse, st);
+        if (rc2) return rc2;
+        if (S->G > 1) {
+            slab_signal_kernel<<<1, 32, 0, st>>>(peers, S->G, S->rank, 1, epoch);
+            slab_wait_kernel<<<1, 32, 0, st>>>(slab_flags(S, S->rank), S->G, 1, epoch);
+        }
+        if (S->timing) cudaEventRecord(S->ev_t[2], st);
+        rc2 = slab_launch(P, S->l_2b, S->area, out, nullptr, inverse, st);
+        if (rc2) return rc2;
+        if (S->timing) cudaEventRecord(S->ev_t[3], st);
+        return cudaGetLastError() == cudaSuccess ? FFTB200_SUCCESS : FFTB200_EXEC_FAILED;
+    }
     if (!P->real) {
         // y axis + exchange (plane chunks) -> x axis on arrived chunks (second stream) -> z axis
         if (S->G > 1) slab_wait_kernel<<<1, 32, 0, st>>>(slab_flags(S, S->rank), S->G, 0, epoch);

@@ -42,7 +42,9 @@ enum TileVariant : int {
                    // a local all-to-all send buffer)
     V_RR_C2R = 6,  // ROW load of L+1 half-spectrum bins, even/odd pre-pass, half-length inverse FFT, ROW store of
                    // 2L reals (the inverse of V_RR_R2C; no reference call site: src/fft.rg is forward-only)
-    V_COUNT = 7
+    V_RC_PEER = 7, // ROW load, COL store scattered over destination buffers by output index k: the exchange of a
+                   // 2-D slab transform (row FFT + global transpose in one pass)
+    V_COUNT = 8
 };
 
 constexpr int MAX_PEERS = 16;
@@ -81,7 +83,8 @@ template <typename T, int L_, int R_, int W_, int VAR_> struct TileTraits {
     static constexpr int T_LINE = L / R;                            // threads per line
     static constexpr int LOG_TL = ilog2c(T_LINE);
     static constexpr int THREADS = T_LINE * W;
-    static constexpr bool LOAD_ROW = (VAR == V_RR || VAR == V_RC || VAR == V_RR_R2C || VAR == V_RR_C2R);
+    static constexpr bool LOAD_ROW =
+        (VAR == V_RR || VAR == V_RC || VAR == V_RR_R2C || VAR == V_RR_C2R || VAR == V_RC_PEER);
     static constexpr bool STORE_ROW = (VAR == V_RR || VAR == V_RR_R2C || VAR == V_RR_C2R);
     static constexpr bool NEED_SMEM = (S > 1) || (VAR == V_RR_R2C) || (VAR == V_RR_C2R);
     static constexpr int SMEM_BYTES = NEED_SMEM ? L * W * (int)sizeof(cplx<T>) : 0;
@@ -299,7 +302,7 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
             const int k = kadd + kmul * ((ul + b * T_LINE) + q * (L / RL));
             C x = v[b * RL + q];
             if (inv) { T s = x.x; x.x = x.y; x.y = s; }
-            if constexpr (VAR == V_CC_PEER) {
+            if constexpr (VAR == V_CC_PEER || VAR == V_RC_PEER) {
                 C *pd = reinterpret_cast<C *>(p.peer[k >> p.peer_shift]) + off;
                 if (ok) pd[(long long)(k & p.peer_mask) * p.out_ls] = x;
             } else {

@@ -33,6 +33,7 @@ FFTB200_DECL_TABLE(tile_table_f64_rc);
 FFTB200_DECL_TABLE(tile_table_f64_r2c);
 FFTB200_DECL_TABLE(tile_table_f64_ccp);
 FFTB200_DECL_TABLE(tile_table_f64_c2r);
+FFTB200_DECL_TABLE(tile_table_f64_rcp);
 FFTB200_DECL_TABLE(tile_table_f32_rr);
 FFTB200_DECL_TABLE(tile_table_f32_cc);
 FFTB200_DECL_TABLE(tile_table_f32_cctw);
@@ -40,5 +41,6 @@ FFTB200_DECL_TABLE(tile_table_f32_rc);
 FFTB200_DECL_TABLE(tile_table_f32_r2c);
 FFTB200_DECL_TABLE(tile_table_f32_ccp);
 FFTB200_DECL_TABLE(tile_table_f32_c2r);
+FFTB200_DECL_TABLE(tile_table_f32_rcp);
 
 }  // namespace fftb200

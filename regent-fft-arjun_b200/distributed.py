@@ -50,7 +50,10 @@ class CudaSlabEngine:
     def __init__(self, shape, ftype, rank, world, device, chunks):
         self.device = torch.device(device)
         with torch.cuda.device(self.device):
-            self.h = _lib.slab_plan(list(shape), ftype, rank, world, chunks)
+            if len(shape) == 2:
+                self.h = _lib.slab_plan_2d(list(shape), ftype, rank, world)
+            else:
+                self.h = _lib.slab_plan(list(shape), ftype, rank, world, chunks)
         self.ftype = ftype
 
     def bind_stream(self):
@@ -217,3 +220,56 @@ class SlabFFT3D:
             dist.barrier(group=self.group)
         if hasattr(self.engine, "destroy"):
             self.engine.destroy()
+
+
+class SlabFFT2D:
+    """One rank's view of a slab-decomposed forward 2-D complex transform of `shape` = (n0, n1):
+    rank r holds in [n0/G][n1] and gets out [n1/G][n0] (FFTW-MPI's transposed-out layout, doc/mpi.texi:443-466).
+    The row FFT's store is the global transpose into the peers' receive slabs over NVLink; execute() is collective."""
+
+    def __init__(self, shape, dtype, rank=None, world=None, device=None, group=None):
+        from . import _dtype
+        self.shape = tuple(int(v) for v in shape)
+        assert len(self.shape) == 2
+        self.dtype = _dtype(dtype)
+        assert not self.dtype.is_real, "2-D slabs are complex-to-complex"
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        n0, n1 = self.shape
+        assert n0 % self.world == 0 and n1 % self.world == 0
+        self.local_in_shape, self.local_out_shape = (n0 // self.world, n1), (n1 // self.world, n0)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        ftype = _lib.C2C if self.dtype.size == 8 else _lib.Z2Z
+        self.engine = CudaSlabEngine(self.shape, ftype, self.rank, self.world, self.device, 1)
+        self.out = torch.empty(self.local_out_shape, dtype=self.dtype.torch, device=self.device)
+        if self.world > 1:
+            ok = 1
+            try:
+                self.engine.connect(group)
+            except _lib.FFTB200Error:
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                raise RuntimeError("2-D slab transforms need peer access between the GPUs (fused exchange only)")
+
+    def execute(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        assert tuple(x.shape) == self.local_in_shape and x.dtype == self.dtype.torch and x.is_contiguous()
+        out = self.out if out is None else out
+        self.engine.fused(x, out)
+        return out
+
+    def gather_natural(self, out: torch.Tensor | None = None) -> np.ndarray:
+        out = self.out if out is None else out
+        if self.world == 1:
+            return out.cpu().numpy().T
+        parts = [torch.empty_like(out) for _ in range(self.world)]
+        dist.all_gather([torch.view_as_real(p) for p in parts], torch.view_as_real(out.contiguous()), group=self.group)
+        return np.concatenate([p.cpu().numpy() for p in parts], axis=0).T
+
+    def destroy(self):
+        if self.world > 1 and dist.is_initialized():
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+        self.engine.destroy()

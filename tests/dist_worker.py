@@ -72,7 +72,10 @@ def main():
     single = a.kind in ("c2c", "r2c")
     full = oracle.synth(shape, np_in, seed=77)
     engine = OracleSlabEngine(shape, world, real) if a.engine == "oracle" else None
-    plan = D.SlabFFT3D(shape, dt_in, rank=rank, world=world, device=dev, mode=a.mode, chunks=a.chunks, engine=engine)
+    if len(shape) == 2:
+        plan = D.SlabFFT2D(shape, dt_in, rank=rank, world=world, device=dev)
+    else:
+        plan = D.SlabFFT3D(shape, dt_in, rank=rank, world=world, device=dev, mode=a.mode, chunks=a.chunks, engine=engine)
     n0l = shape[0] // world
     x = torch.from_numpy(np.ascontiguousarray(full[rank * n0l:(rank + 1) * n0l])).to(dev)
     x_keep = x.clone()
@@ -87,7 +90,7 @@ def main():
     tol = oracle.tolerance(int(np.prod(shape)), single)
     assert err <= tol, f"rank {rank}: rel-L2 {err:.3e} > {tol:.3e}"
     assert torch.equal(x, x_keep), "input slab was modified"
-    assert got.shape == (shape[0], shape[1], shape[2] // 2 + 1 if real else shape[2])
+    assert got.shape == (tuple(shape) if len(shape) == 2 else (shape[0], shape[1], shape[2] // 2 + 1 if real else shape[2]))
     plan.destroy()
     dist.barrier()
     if rank == 0:

@@ -131,6 +131,36 @@ def test_slab_fused_single_rank_plane_chunks(fft, oracle, kind, planes, monkeypa
 
 
 @pytest.mark.gpu
+def test_slab_2d_single_rank(fft, oracle):
+    """2-D slab plan with G = 1: row pass into the (local) receive slab transposed, row pass back"""
+    from regent_fft_arjun_b200 import distributed as D
+    for kind, shape in [("z2z", (64, 128)), ("c2c", (256, 32)), ("z2z", (1024, 16)), ("z2z", (8, 4096))]:
+        dt = {"z2z": fft.complex64, "c2c": fft.complex32}[kind]
+        np_in = {"z2z": np.complex128, "c2c": np.complex64}[kind]
+        x = oracle.synth(shape, np_in, seed=91)
+        plan = D.SlabFFT2D(shape, dt, rank=0, world=1, device="cuda:0")
+        xd = torch.from_numpy(x).cuda()
+        for _ in range(2):
+            plan.execute(xd)
+        torch.cuda.synchronize()
+        got = plan.gather_natural()
+        plan.destroy()
+        assert np.array_equal(xd.cpu().numpy(), x)
+        assert oracle.rel_l2(got, oracle.port_dft(x.astype(np.complex128))) <= oracle.tolerance(int(np.prod(shape)), kind == "c2c")
+
+
+@pytest.mark.gpu
+def test_slab_2d_multi_gpu(built):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    world = 2 if n < 4 else 4
+    for kind, shape in [("z2z", "256,512"), ("c2c", "1024,128"), ("z2z", "2048,4096")]:
+        _torchrun(world, ["--backend", "nccl", "--engine", "cuda", "--mode", "p2p", "--kind", kind, "--shape", shape,
+                          "--reps", "3"], port=29850 + len(shape))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["nccl", "p2p"])
 def test_slab_multi_gpu(built, mode):
     n = torch.cuda.device_count()

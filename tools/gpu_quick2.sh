@@ -1,2 +1,6 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "inverse_real or golden or random or properties" 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_slab.py -m gpu -x -q -k "2d" 2>&1 | tail -8
+python - <<'PY'
+import os, sys, json, torch, numpy as np
+sys.path.insert(0, os.getcwd())
+PY
