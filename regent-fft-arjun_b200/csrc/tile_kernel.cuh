@@ -339,7 +339,27 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
     const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);
     const bool inv = p.inverse != 0;
 
-    // ------------------------------------------------------------------ L2 prefetch of a future tile
+    C v[R];
+
+    // ------------------------------------------------------------------ stage 1: HBM -> registers
+    const int w1 = TR::LOAD_ROW ? w_row : w_col;
+    const int u1 = TR::LOAD_ROW ? u_row : u_col;
+    {
+        const bool ok = (i0 + w1) < p.n_inner;
+        const C *src = gin + (long long)(i0 + w1) * p.in_is + (long long)u1 * p.in_ls;
+#pragma unroll
+        for (int d = 0; d < R; ++d) {
+            C x = mk<T>((T)0, (T)0);
+            if (ok) {
+                if constexpr (DATA_CG) x = __ldcg(src + (long long)(d * T_LINE) * p.in_ls);
+                else x = ld_data<T>(src + (long long)(d * T_LINE) * p.in_ls);
+            }
+            if (inv && VAR != V_RR_C2R) { T s = x.x; x.x = x.y; x.y = s; }
+            v[d] = x;
+        }
+    }
+
+    // ------------------------------------------------------------------ L2 prefetch of a future tile (after this tile's own loads are in flight)
     if (p.prefetch_tiles > 0) {
         const int ft = tile + p.prefetch_tiles;
         if (ft < p.n_tiles) {
@@ -370,25 +390,6 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
         }
     }
 
-    C v[R];
-
-    // ------------------------------------------------------------------ stage 1: HBM -> registers
-    const int w1 = TR::LOAD_ROW ? w_row : w_col;
-    const int u1 = TR::LOAD_ROW ? u_row : u_col;
-    {
-        const bool ok = (i0 + w1) < p.n_inner;
-        const C *src = gin + (long long)(i0 + w1) * p.in_is + (long long)u1 * p.in_ls;
-#pragma unroll
-        for (int d = 0; d < R; ++d) {
-            C x = mk<T>((T)0, (T)0);
-            if (ok) {
-                if constexpr (DATA_CG) x = __ldcg(src + (long long)(d * T_LINE) * p.in_ls);
-                else x = ld_data<T>(src + (long long)(d * T_LINE) * p.in_ls);
-            }
-            if (inv && VAR != V_RR_C2R) { T s = x.x; x.x = x.y; x.y = s; }
-            v[d] = x;
-        }
-    }
 
     if constexpr (VAR == V_RR_C2R) {
         // ---- even/odd pre-pass: from the half spectrum X[0..L] of 2L reals build
