@@ -92,7 +92,11 @@ static int env_int_or(const char *name, int dflt) {
 }
 
 // one launch of a tile pass; cluster kernels go through cudaLaunchKernelEx with the cluster dimension
-static cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st, const TileParams &tp) {
+static cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st, const TileParams &tp, bool bulk = false) {
+    if (bulk && ki->fn_bulk) {
+        ki->fn_bulk<<<grid, ki->threads, ki->smem_bytes, st>>>(tp);
+        return cudaGetLastError();
+    }
     if (tp.ticket) {
         const cudaError_t e = cudaMemsetAsync(tp.ticket, 0, sizeof(unsigned), st);
         if (e != cudaSuccess) return e;
@@ -139,6 +143,7 @@ struct Launch {
     // common
     long long in_off = 0, out_off = 0;  // element offsets added to the source / destination base (chunked passes)
     unsigned *ticket = nullptr;         // persistent (capped) launches: dynamic tile counter, zeroed before every launch
+    bool bulk = false;                  // launch ki->fn_bulk (tile fetched by the TMA engine)
     int src = BUF_IN, dst = BUF_OUT;
     unsigned grid = 0;
     unsigned long long algo_bytes = 0;
@@ -389,6 +394,17 @@ static bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long 
         }
     }
     tp.ticket = nullptr;
+    {
+        // FFTB200_BULK=1: fetch column-pass tiles with the TMA engine; =2: only where the line stride exceeds 64 KiB
+        const int mode = env_int_or("FFTB200_BULK", 0);
+        const bool far = in_ls * (long long)(P->prec ? 16 : 8) > 65536;
+        if (mode > 0 && ki->fn_bulk && parts == 1 && lv[0].n % ki->W == 0 && (mode == 1 || far)) {
+            ln.bulk = true;
+            if (ki->smem_bytes > 48 * 1024)
+                cudaFuncSetAttribute((const void *)ki->fn_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, ki->smem_bytes);
+            cudaGetLastError();
+        }
+    }
     tp.prefetch_tiles = 0;
     {
         // L2 prefetch of the tile that will run next in this CTA slot (distance = CTAs resident on the GPU).
@@ -871,7 +887,7 @@ static int run_launches(Plan *P, const void *in, void *out, int inverse) {
             tp.out = dst;
             tp.inverse = inverse;
             tp.ticket = ln.ticket;
-            ce = launch_tile(ln.ki, ln.grid, P->stream, tp);
+            ce = launch_tile(ln.ki, ln.grid, P->stream, tp, ln.bulk);
         } else if (ln.kind == Launch::FUSED) {
             FusedParams fp;
             fp.a = ln.tp;

@@ -314,8 +314,11 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
 
 // DATA_CG: read the tile with ld.global.cg (L2-coherent).  Needed when the data was written earlier in the
 // SAME kernel by other SMs (fused two-axis pass): the read-only / L1 path could return stale lines.
-template <typename T, int L, int R, int W, int VAR, bool DATA_CG = false>
-__device__ __forceinline__ void fft_tile_body(const TileParams &p, const int tile, unsigned char *smem_raw) {
+// BULK: the tile is fetched by the TMA engine (cp.async.bulk, one 128-byte row segment per request, completion
+// counted by an mbarrier) straight into shared memory instead of through registers; column passes only.
+template <typename T, int L, int R, int W, int VAR, bool DATA_CG = false, bool BULK = false>
+__device__ __forceinline__ void fft_tile_body(const TileParams &p, const int tile, unsigned char *smem_raw,
+                                              const unsigned mbar = 0) {
     using TR = TileTraits<T, L, R, W, VAR>;
     using C = cplx<T>;
     constexpr int S = TR::S;
@@ -344,7 +347,34 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
     // ------------------------------------------------------------------ stage 1: HBM -> registers
     const int w1 = TR::LOAD_ROW ? w_row : w_col;
     const int u1 = TR::LOAD_ROW ? u_row : u_col;
-    {
+    if constexpr (BULK) {
+        static_assert(!TR::LOAD_ROW && !TR::SWIZZLED, "bulk loads fill the unswizzled column-pass layout");
+        constexpr unsigned ROW_BYTES = (unsigned)(W * sizeof(C));
+        const unsigned sm_addr = (unsigned)__cvta_generic_to_shared(sm);
+        if (t == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)L * ROW_BYTES) : "memory");
+        const C *src0 = gin + (long long)i0 * p.in_is;  // whole tiles only (the plan guarantees it)
+        for (int r = t; r < L; r += TR::THREADS) {
+            const C *row = src0 + (long long)r * p.in_ls;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             sm_addr + (unsigned)r * ROW_BYTES),
+                         "l"(row), "r"(ROW_BYTES), "r"(mbar)
+                         : "memory");
+        }
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done)
+                         : "r"(mbar), "r"(0u)
+                         : "memory");
+        }
+#pragma unroll
+        for (int d = 0; d < R; ++d) {
+            C x = sm[((u1 + d * T_LINE) << LOG_W) | w1];
+            if (inv) { T s = x.x; x.x = x.y; x.y = s; }
+            v[d] = x;
+        }
+    } else {
         const bool ok = (i0 + w1) < p.n_inner;
         const C *src = gin + (long long)(i0 + w1) * p.in_is + (long long)u1 * p.in_ls;
 #pragma unroll
@@ -591,6 +621,28 @@ fft_fused_ab_kernel(const FusedParams p) {
         __syncthreads();  // next ticket visible; shared memory of this tile free
         cur ^= 1;
     }
+}
+
+// Column pass whose tile is fetched by the TMA engine (see BULK above); one tile per CTA.
+template <typename T, int L, int R, int W, int VAR>
+__global__ void __launch_bounds__(TileTraits<T, L, R, W, VAR>::THREADS, TileTraits<T, L, R, W, VAR>::MIN_CTAS)
+fft_tile_bulk_kernel(const TileParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar_storage;
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(&mbar_storage);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    fft_tile_body<T, L, R, W, VAR, false, true>(p, (int)blockIdx.x, smem_raw, mbar);
+}
+
+template <typename T, int L, int R, int W, int VAR> constexpr void (*bulk_kernel_or_null())(const TileParams) {
+    if constexpr (VAR == V_CC && !TileTraits<T, L, R, W, VAR>::SWIZZLED && TileTraits<T, L, R, W, VAR>::S > 1)
+        return &fft_tile_bulk_kernel<T, L, R, W, VAR>;
+    else
+        return nullptr;
 }
 
 // ---------------------------------------------------------------------------------------------

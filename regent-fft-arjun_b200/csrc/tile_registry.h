@@ -9,6 +9,7 @@ struct TileKernelInfo {
     int L, R, W, threads, smem_bytes;
     int cluster;  // CTAs per thread-block cluster (1 = ordinary launch); L = cluster * (length one CTA holds)
     int split;    // independent CTAs per tile (fft_split_kernel; 1 otherwise); L = split * (length one CTA holds)
+    void (*fn_bulk)(const TileParams);  // same pass with the tile fetched by the TMA engine (column passes), or nullptr
 };
 
 struct FusedKernelInfo {
