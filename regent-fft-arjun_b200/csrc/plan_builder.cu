@@ -1,0 +1,671 @@
+// plan_builder.cu — turns cufftPlanMany-style arguments into a list of kernel launches (include/fft_b200.h).
+//
+// This is the layer that replaces cuFFT behind Regent-FFT's GPU branch
+// (reference src/fft.rg:233-242, 389-398, 571-580, 638).  A plan is a short list of kernel
+// launches ("passes"); every pass is one HBM round trip over one axis:
+//
+//   3-D C2C  [n0][n1][n2] : ROW pass over n2 (in -> out), COL pass over n1, COL pass over n0 (in place)
+//   R2C                   : the first pass is the fused half-length FFT + even/odd post-pass,
+//                           later passes run over n_last/2+1 columns
+//   1-D N > one tile      : four-step, N = N1*N2(*N3): COL+twiddle pass(es), then a transposing
+//                           ROW->COL pass, through the plan's work buffer
+//   anything else         : generic global-memory path (generic_kernels.cuh)
+//
+// No CPU fallback exists: if a kernel cannot be launched the call returns an error code.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "plan_internal.h"
+
+namespace fftb200 {
+
+// ------------------------------------------------------------------------------------------
+// twiddles: w_n^m = exp(-2*pi*i*m/n), octant-reduced like fftw-3.3.8/kernel/trig.c:57-80, but
+// evaluated in long double before rounding (the accuracy contract of SURVEY.md §8 a10)
+// ------------------------------------------------------------------------------------------
+static void twiddle(long long m, long long n, double *re, double *im) {
+    static const long double K2PI = 6.2831853071795864769252867665590057683943388L;
+    unsigned octant = 0;
+    long long quarter_n = n;
+    n *= 4;
+    m *= 4;
+    if (m < 0) m += n;
+    if (m > n - m) { m = n - m; octant |= 4; }
+    if (m - quarter_n > 0) { m = m - quarter_n; octant |= 2; }
+    if (m > quarter_n - m) { m = quarter_n - m; octant |= 1; }
+    const long double theta = (K2PI * (long double)m) / (long double)n;
+    long double c = cosl(theta), s = sinl(theta), t;
+    if (octant & 1) { t = c; c = s; s = t; }
+    if (octant & 2) { t = c; c = -s; s = t; }
+    if (octant & 4) { s = -s; }
+    *re = (double)c;
+    *im = (double)(-s);  // forward sign
+}
+
+int env_int_or(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------
+// device tables
+// ------------------------------------------------------------------------------------------
+void *Builder::upload(const void *host, size_t bytes) {
+    void *d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { err = FFTB200_ALLOC_FAILED; cudaGetLastError(); return nullptr; }
+    P->dev_allocs.push_back(d);
+    if (cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { err = FFTB200_SETUP_FAILED; cudaGetLastError(); return nullptr; }
+    return d;
+}
+
+void *Builder::table(long long n, long long count, bool force_double, long long step) {
+    const int kind = (force_double ? 1 : 0) + (step != 1 ? 2 : 0);
+    auto key = std::make_pair(std::make_pair(kind, n), count);
+    if (step == 1) {
+        auto it = cache.find(key);
+        if (it != cache.end()) return it->second;
+    }
+    void *d = nullptr;
+    if (P->prec == 1 || force_double) {
+        std::vector<double> h(2 * (size_t)count);
+        for (long long k = 0; k < count; ++k) twiddle((k * step) % n, n, &h[2 * k], &h[2 * k + 1]);
+        d = upload(h.data(), h.size() * sizeof(double));
+    } else {
+        std::vector<float> h(2 * (size_t)count);
+        for (long long k = 0; k < count; ++k) {
+            double re, im;
+            twiddle((k * step) % n, n, &re, &im);
+            h[2 * k] = (float)re;
+            h[2 * k + 1] = (float)im;
+        }
+        d = upload(h.data(), h.size() * sizeof(float));
+    }
+    if (step == 1) cache[key] = d;
+    return d;
+}
+
+void *Builder::alloc(size_t bytes) {
+    void *d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { err = FFTB200_ALLOC_FAILED; cudaGetLastError(); return nullptr; }
+    P->dev_allocs.push_back(d);
+    return d;
+}
+
+bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+int ilog2ll(long long v) { int l = 0; while ((1ll << (l + 1)) <= v) ++l; return l; }
+
+
+// merge adjacent index levels that are dense in both buffers
+static void merge_levels(std::vector<Level> &lv) {
+    std::vector<Level> out;
+    for (size_t i = 0; i < lv.size(); ++i) {
+        const Level &l = lv[i];
+        // a unit-stride level of extent 1 stays: it is the tile's inner index (ragged last chunk of a slab pass)
+        if (l.n == 1 && !(i == 0 && l.is == 1 && l.os == 1 && lv.size() > 1)) continue;
+        if (!out.empty() && l.is == out.back().n * out.back().is && l.os == out.back().n * out.back().os)
+            out.back().n *= l.n;
+        else
+            out.push_back(l);
+    }
+    lv.swap(out);
+}
+
+static const char *variant_name(int v) {
+    static const char *names[] = {"row", "col", "col+twiddle", "row->col", "r2c-row", "col->peers", "c2r-row", "row->peers"};
+    return names[v];
+}
+
+// Add one tile pass.  levels: non-axis index levels, fastest first (levels[0] = lines of a tile).
+bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long long out_ls, std::vector<Level> lv,
+                          int src, int dst, long long twN /* four-step N */, const char *what) {
+    Plan *P = B.P;
+    const TileKernelInfo *ki = find_tile_kernel(P->prec, variant, L);
+    if (!ki) return false;
+    merge_levels(lv);
+    if (lv.size() > 3) return false;
+    while (lv.size() < 3) lv.push_back({1, 0, 0});
+    const bool load_row =
+        (variant == V_RR || variant == V_RC || variant == V_RR_R2C || variant == V_RR_C2R || variant == V_RC_PEER);
+    const bool store_row = (variant == V_RR || variant == V_RR_R2C || variant == V_RR_C2R);
+    if (load_row ? (in_ls != 1) : (lv[0].n > 1 && lv[0].is != 1)) return false;
+    if (store_row ? (out_ls != 1) : (lv[0].n > 1 && lv[0].os != 1)) return false;
+    if (lv[0].n > 0x7fffffffll || lv[1].n > 0x7fffffffll) return false;
+
+    Launch ln;
+    ln.kind = Launch::TILE;
+    ln.ki = ki;
+    ln.variant = variant;
+    ln.src = src;
+    ln.dst = dst;
+    TileParams &tp = ln.tp;
+    const int parts = ki->cluster * ki->split;  // CTAs that share one line
+    tp.tw = (L > ki->R) ? B.table(L / parts, L / parts, false) : nullptr;  // w_LL of the CTA-local stages
+    tp.tw_aux = nullptr;
+    if (parts > 1) tp.tw_aux = B.table(L, L, false);  // cross-CTA stage twiddles w_L
+    if (variant == V_RR_R2C) tp.tw_aux = B.table(2ll * L, L / 2 + 1, false);
+    if (variant == V_RR_C2R) tp.tw_aux = B.table(2ll * L, L, false);
+    tp.tw4_hi = tp.tw4_lo = nullptr;
+    tp.tw4_shift = 0;
+    tp.tw4_mask = 0;
+    if (variant == V_CC_TW) {
+        const int bits = ilog2ll(twN);
+        const int sh = (bits + 1) / 2;
+        tp.tw4_shift = sh;
+        tp.tw4_mask = (1 << sh) - 1;
+        tp.tw4_lo = (const double2 *)B.table(twN, 1ll << sh, true);
+        tp.tw4_hi = (const double2 *)B.table(twN, (twN >> sh) + 1, true, 1ll << sh);
+    }
+    tp.in_ls = in_ls;
+    tp.out_ls = out_ls;
+    tp.n_inner = (int)lv[0].n;
+    tp.in_is = lv[0].is;
+    tp.out_is = lv[0].os;
+    tp.n_o2 = (int)lv[1].n;
+    tp.in_os2 = lv[1].is;
+    tp.out_os2 = lv[1].os;
+    tp.in_os1 = lv[2].is;
+    tp.out_os1 = lv[2].os;
+    tp.tiles_per_outer = (int)((lv[0].n + ki->W - 1) / ki->W);
+    tp.inverse = 0;
+    const long long tiles = (long long)tp.tiles_per_outer * lv[1].n * lv[2].n;
+    if (tiles <= 0 || tiles > 0x7fffffffll) return false;
+    if (tiles * parts > 0x7fffffffll) return false;
+    ln.grid = (unsigned)(tiles * parts);
+    tp.n_tiles = (int)tiles;
+    {
+        // FFTB200_GRID_CAP=n (tuning): run single-CTA passes persistently on at most n CTAs
+        const int cap = env_int_or("FFTB200_GRID_CAP", 0);
+        if (cap > 0 && ki->cluster == 1 && variant == V_CC_PEER && ln.grid > (unsigned)cap) {
+            ln.grid = (unsigned)cap;
+            ln.ticket = (unsigned *)B.alloc(sizeof(unsigned));
+        }
+    }
+    tp.ticket = nullptr;
+    {
+        // FFTB200_BULK=1: fetch column-pass tiles with the TMA engine; =2: only where the line stride exceeds 64 KiB
+        const int mode = env_int_or("FFTB200_BULK", 0);
+        const bool far = in_ls * (long long)(P->prec ? 16 : 8) > 65536;
+        if (mode > 0 && ki->fn_bulk && parts == 1 && lv[0].n % ki->W == 0 && (mode == 1 || far)) {
+            ln.bulk = true;
+            if (ki->smem_bytes > 48 * 1024)
+                cudaFuncSetAttribute((const void *)ki->fn_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, ki->smem_bytes);
+            cudaGetLastError();
+        }
+    }
+    tp.prefetch_tiles = 0;
+    {
+        // L2 prefetch of the tile that will run next in this CTA slot (distance = CTAs resident on the GPU).
+        // Measured on B200 (512^3): strided-axis passes whose lines stay inside a few 2 MiB pages gain ~9 %
+        // (fp64 y axis 0.760 -> 0.692 ms, 6.2 TB/s); passes with a multi-MiB line stride lose (z axis
+        // 0.86 -> 1.12 ms) and contiguous-axis passes do not change, so only the first kind prefetches.
+        // FFTB200_PREFETCH=0 switches it off, =k forces distance k on every single-CTA pass (tuning).
+        const int forced = env_int_or("FFTB200_PREFETCH", -1);
+        const bool col_load = !load_row;
+        const bool page_local = in_ls * (long long)(P->prec ? 16 : 8) <= 65536;
+        const int k = forced >= 0 ? forced : ((col_load && page_local) ? 1 : 0);
+        if (k > 0 && ki->cluster == 1) {
+            int sms = 148, per_sm = 1;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P->device);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)ki->fn, ki->threads, ki->smem_bytes) != cudaSuccess)
+                cudaGetLastError();
+            tp.prefetch_tiles = k * sms * (per_sm > 0 ? per_sm : 1) / ki->split;
+        }
+    }
+    const long long lines = lv[0].n * lv[1].n * lv[2].n;
+    const size_t ce = P->prec ? 16 : 8;
+    if (variant == V_RR_R2C || variant == V_RR_C2R)
+        ln.algo_bytes = (unsigned long long)lines * ((unsigned long long)L * ce + (unsigned long long)(L + 1) * ce);
+    else
+        ln.algo_bytes = (unsigned long long)lines * L * ce * 2ull;
+    char buf[256];
+    snprintf(buf, sizeof buf, "tile %-11s %s L=%d R=%d W=%d threads=%d smem=%d cluster=%d split=%d lines=%lld tiles=%lld (%s)",
+             variant_name(variant), P->prec ? "fp64" : "fp32", L, ki->R, ki->W, ki->threads, ki->smem_bytes, ki->cluster,
+             ki->split, lines, tiles, what);
+    ln.desc = buf;
+    if (ki->smem_bytes > 48 * 1024) {
+        if (cudaFuncSetAttribute((const void *)ki->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ki->smem_bytes) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            B.err = FFTB200_SETUP_FAILED;
+            return false;
+        }
+    }
+    P->launches.push_back(ln);
+    return B.err == FFTB200_SUCCESS;
+}
+
+// split N = 2^k (too long for one tile) into 2 or 3 factors, each tile-friendly
+static std::vector<int> split_1d(long long N, int prec) {
+    const int k = ilog2ll(N);
+    // COL passes want L*W*elt <= 64 KiB with 128-byte segments: L <= 512
+    std::vector<int> f;
+    if (k <= 18) {
+        const int a = k / 2;
+        f = {1 << a, 1 << (k - a)};
+    } else if (k <= 27) {
+        const int a = k / 3, b = (k - a) / 2;
+        f = {1 << a, 1 << b, 1 << (k - a - b)};
+    } else {
+        return f;
+    }
+    (void)prec;
+    return f;
+}
+
+// Fuse the contiguous-axis pass and the following strided-axis pass into one persistent kernel when both
+// use the same CTA shape and the first pass's tiles enumerate whole planes in order (dense layouts).
+// FFTB200_NO_FUSE=1 keeps the separate passes (benchmarking only).
+static void try_fuse_first_two(Builder &B) {
+    Plan *P = B.P;
+    if (P->real || P->launches.size() < 2) return;
+    // Opt-in (FFTB200_FUSE=1).  Measured on B200 at 512^3 fp64: the fused kernel cuts HBM traffic of the two
+    // passes from 8.5 GB to 4.25 GB (ncu dram__bytes), but both forms are bound by per-tile latency at two
+    // CTAs per SM, not by HBM, and the ticket/flag traffic makes the fused form ~5 % slower (1.59 vs 1.51 ms).
+    const char *fu = getenv("FFTB200_FUSE");
+    if (!(fu && *fu && *fu != '0')) return;
+    Launch &a = P->launches[0], &b = P->launches[1];
+    if (a.kind != Launch::TILE || b.kind != Launch::TILE || a.variant != V_RR || b.variant != V_CC) return;
+    if (a.ki->cluster != 1 || b.ki->cluster != 1 || a.dst != BUF_OUT || b.src != BUF_OUT || b.dst != BUF_OUT) return;
+    const FusedKernelInfo *fk = find_fused_kernel(P->prec, a.ki->L, b.ki->L);
+    if (!fk) return;
+    if (a.ki->R != fk->RA || a.ki->W != fk->WA || b.ki->R != fk->RB || b.ki->W != fk->WB) return;
+    if (a.tp.n_tiles != a.tp.tiles_per_outer) return;  // pass A must be one dense run of rows
+    const long long planes = b.tp.n_tiles / b.tp.tiles_per_outer;
+    if (planes < 8 || a.tp.n_tiles % planes) return;
+    const long long ta_plane = a.tp.n_tiles / planes, tb_plane = b.tp.tiles_per_outer;
+    // rows of pass A per plane must equal the line length of pass B
+    if (ta_plane * a.ki->W != b.ki->L) return;
+    const long long want_tiles = env_int_or("FFTB200_FUSE_TILES", 128);  // benchmarking override
+    long long Pg = (want_tiles + ta_plane - 1) / ta_plane;
+    if (Pg < 1) Pg = 1;
+    while (Pg < planes && planes % Pg) ++Pg;
+    if (planes % Pg) return;
+    const long long n_groups = planes / Pg;
+    const int lag = env_int_or("FFTB200_FUSE_LAG", 2);
+    if (lag < 1 || n_groups < 2 * lag) return;
+    unsigned *counters = (unsigned *)B.alloc(sizeof(unsigned) * (size_t)(1 + n_groups));
+    if (!counters) return;
+    int sms = 148, per_sm = fk->min_ctas;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P->device);
+    if (fk->smem_bytes > 48 * 1024 &&
+        cudaFuncSetAttribute((const void *)fk->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fk->smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fk->fn, fk->threads, fk->smem_bytes) != cudaSuccess ||
+        per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    Launch f = a;
+    f.kind = Launch::FUSED;
+    f.fk = fk;
+    f.tp_b = b.tp;
+    f.counters = counters;
+    f.tiles_a = (int)(ta_plane * Pg);
+    f.tiles_b = (int)(tb_plane * Pg);
+    f.n_groups = (int)n_groups;
+    f.lag = lag;
+    const long long total = (long long)(f.tiles_a + f.tiles_b) * n_groups;
+    f.grid = (unsigned)std::min<long long>(total, (long long)sms * per_sm);
+    f.src = a.src;
+    f.dst = BUF_OUT;
+    // compulsory HBM traffic of the fused pair: read the input once, write the result once
+    f.algo_bytes = a.algo_bytes;
+    char buf[320];
+    snprintf(buf, sizeof buf,
+             "fused row+col    %s L=%dx%d threads=%d smem=%d persistent grid=%u (%d CTAs/SM) groups=%d x %lld planes lag=%d "
+             "lines=%lld (last axis + next axis through L2)",
+             P->prec ? "fp64" : "fp32", a.ki->L, b.ki->L, fk->threads, fk->smem_bytes, f.grid, per_sm, f.n_groups, Pg, lag,
+             (long long)a.tp.n_tiles * a.ki->W);
+    f.desc = buf;
+    P->launches.erase(P->launches.begin(), P->launches.begin() + 2);
+    P->launches.insert(P->launches.begin(), f);
+}
+
+// ------------------------------------------------------------------------------------------
+// fast plan (power-of-two, unit element stride)
+// ------------------------------------------------------------------------------------------
+static bool build_fast(Builder &B) {
+    Plan *P = B.P;
+    const int rank = P->rank;
+    const long long *n = P->n;
+    const int maxL = max_tile_length(P->prec);
+    for (int d = 0; d < rank; ++d)
+        if (!is_pow2(n[d])) return false;
+    if (P->in_stride[rank] != 1 || P->out_stride[rank] != 1) return false;
+    long long total = 1;
+    for (int d = 0; d < rank; ++d) total *= n[d];
+    if (total == 1) return false;  // nothing to transform: generic path copies
+
+    // output extents (last cut to n/2+1 for real input)
+    long long nout[3];
+    for (int d = 0; d < rank; ++d) nout[d] = n[d];
+    const int last = rank - 1;
+    if (P->real) {
+        if (n[last] < 4 || n[last] / 2 > maxL) return false;
+        for (int d = 0; d <= rank; ++d)
+            if (d != rank && (P->in_stride[d] & 1)) return false;  // rows must start on a complex boundary
+        nout[last] = n[last] / 2 + 1;
+    }
+
+    auto levels_for = [&](int axis, bool first_pass) {
+        // fastest first: dims after the axis (reverse), dims before the axis (reverse), batch
+        std::vector<Level> lv;
+        for (int d = rank - 1; d >= 0; --d) {
+            if (d == axis) continue;
+            Level l;
+            l.n = first_pass ? n[d] : nout[d];
+            l.is = first_pass ? P->in_stride[d + 1] : P->out_stride[d + 1];
+            l.os = P->out_stride[d + 1];
+            lv.push_back(l);
+        }
+        Level b;
+        b.n = P->batch;
+        b.is = first_pass ? P->in_stride[0] : P->out_stride[0];
+        b.os = P->out_stride[0];
+        lv.push_back(b);
+        return lv;
+    };
+
+    // ---- last axis (contiguous) ----
+    bool first = true;
+    if (P->real) {
+        std::vector<Level> lv = levels_for(last, true);
+        for (Level &l : lv) l.is /= 2;  // input addressed as packed complex pairs
+        if (!add_tile_pass(B, V_RR_R2C, (int)(n[last] / 2), 1, 1, lv, BUF_IN, BUF_OUT, 0, "axis r2c")) return false;
+        first = false;
+    } else if (n[last] > 1) {
+        if (n[last] <= maxL) {
+            if (!add_tile_pass(B, V_RR, (int)n[last], 1, 1, levels_for(last, true), BUF_IN, BUF_OUT, 0, "last axis"))
+                return false;
+            first = false;
+        } else {
+            // four-step: only as the sole transformed axis of the plan
+            for (int d = 0; d < last; ++d)
+                if (n[d] != 1) return false;
+            std::vector<int> f = split_1d(n[last], P->prec);
+            if (f.empty()) return false;
+            const long long N = n[last];
+            const size_t ce = P->prec ? 16 : 8;
+            P->work_bytes = (size_t)N * P->batch * ce;
+            P->work[0] = B.alloc(P->work_bytes);
+            if (!P->work[0]) return false;
+            const long long bi = P->in_stride[0], bo = P->out_stride[0];
+            if (f.size() == 2) {
+                const long long N1 = f[0], M = f[1];
+                if (!add_tile_pass(B, V_CC_TW, (int)N1, M, M, {{M, 1, 1}, {P->batch, bi, N}}, BUF_IN, BUF_WORK0, N,
+                                   "four-step 1/2"))
+                    return false;
+                if (!add_tile_pass(B, V_RC, (int)M, 1, N1, {{N1, M, 1}, {P->batch, N, bo}}, BUF_WORK0, BUF_OUT, 0,
+                                   "four-step 2/2"))
+                    return false;
+            } else {
+                const long long N1 = f[0], N2 = f[1], N3 = f[2], M = N2 * N3;
+                if (!add_tile_pass(B, V_CC_TW, (int)N1, M, M, {{M, 1, 1}, {P->batch, bi, N}}, BUF_IN, BUF_WORK0, N,
+                                   "six-step 1/3"))
+                    return false;
+                if (!add_tile_pass(B, V_CC_TW, (int)N2, N3, N3, {{N3, 1, 1}, {N1, M, M}, {P->batch, N, N}}, BUF_WORK0,
+                                   BUF_WORK0, M, "six-step 2/3"))
+                    return false;
+                if (!add_tile_pass(B, V_RC, (int)N3, 1, N1 * N2, {{N1, M, 1}, {N2, N3, N1}, {P->batch, N, bo}},
+                                   BUF_WORK0, BUF_OUT, 0, "six-step 3/3"))
+                    return false;
+            }
+            P->inplace_ok = true;  // every pass goes through the work buffer
+            return true;
+        }
+    }
+
+    // ---- remaining axes (strided) ----
+    for (int axis = last - 1; axis >= 0; --axis) {
+        if (n[axis] == 1) continue;
+        if (n[axis] > maxL) return false;
+        std::vector<Level> lv = levels_for(axis, first);
+        const long long in_ls = first ? P->in_stride[axis + 1] : P->out_stride[axis + 1];
+        const long long out_ls = P->out_stride[axis + 1];
+        if (!add_tile_pass(B, V_CC, (int)n[axis], in_ls, out_ls, lv, first ? BUF_IN : BUF_OUT, BUF_OUT, 0,
+                           "strided axis"))
+            return false;
+        first = false;
+    }
+    if (first) return false;
+    try_fuse_first_two(B);
+    // in place is safe when every pass reads and writes the same addresses tile by tile
+    bool same = !P->real;
+    for (int d = 0; d <= rank; ++d) same = same && (P->in_stride[d] == P->out_stride[d]);
+    P->inplace_ok = same;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// inverse real plan (C2R / Z2D): backward COL passes over the n_last/2+1 columns (through a work buffer, so the
+// input survives), then the fused even/odd pre-pass + half-length backward FFT on the last axis
+// ------------------------------------------------------------------------------------------
+static bool build_c2r(Builder &B) {
+    Plan *P = B.P;
+    const int rank = P->rank, last = rank - 1;
+    const long long *n = P->n;
+    const int maxL = max_tile_length(P->prec);
+    for (int d = 0; d < rank; ++d)
+        if (!is_pow2(n[d])) return false;
+    if (P->in_stride[rank] != 1 || P->out_stride[rank] != 1) return false;
+    if (n[last] < 4 || n[last] / 2 > maxL) return false;
+    for (int d = 0; d < rank; ++d)
+        if (P->out_stride[d] & 1) return false;  // output rows / batches must start on a pair of reals
+    const long long nc = n[last] / 2 + 1;
+    long long outer_axes = 1;
+    for (int d = 0; d < last; ++d) {
+        if (n[d] > maxL) return false;
+        outer_axes *= n[d];
+    }
+    const size_t ce = P->prec ? 16 : 8;
+    int cur = BUF_IN;
+    long long cs[4];  // strides of the current complex array, [batch, d0.., d_last]
+    for (int d = 0; d <= rank; ++d) cs[d] = P->in_stride[d];
+    if (outer_axes > 1) {
+        long long ws[4];  // dense work layout [batch][n0]..[nc]
+        ws[rank] = 1;
+        for (int d = rank - 1; d >= 0; --d) ws[d] = ws[d + 1] * (d == last ? nc : n[d]);
+        const long long total = ws[0] * P->batch;
+        P->work_bytes = (size_t)total * ce;
+        P->work[0] = B.alloc(P->work_bytes);
+        if (!P->work[0]) return false;
+        for (int axis = last - 1; axis >= 0; --axis) {
+            if (n[axis] == 1) continue;
+            std::vector<Level> lv;
+            for (int d = rank - 1; d >= 0; --d) {
+                if (d == axis) continue;
+                lv.push_back({d == last ? nc : n[d], cs[d + 1], ws[d + 1]});
+            }
+            lv.push_back({(long long)P->batch, cs[0], ws[0]});
+            if (!add_tile_pass(B, V_CC, (int)n[axis], cs[axis + 1], ws[axis + 1], lv, cur, BUF_WORK0, 0, "strided axis (backward)"))
+                return false;
+            cur = BUF_WORK0;
+            for (int d = 0; d <= rank; ++d) cs[d] = ws[d];
+        }
+    }
+    // last axis: lines of nc complex -> n_last reals (addressed as n_last/2 complex pairs)
+    std::vector<Level> lv;
+    for (int d = last - 1; d >= 0; --d) lv.push_back({n[d], cs[d + 1], P->out_stride[d + 1] / 2});
+    lv.push_back({(long long)P->batch, cs[0], P->out_stride[0] / 2});
+    if (!add_tile_pass(B, V_RR_C2R, (int)(n[last] / 2), 1, 1, lv, cur, BUF_OUT, 0, "axis c2r")) return false;
+    P->inplace_ok = false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic plan
+// ------------------------------------------------------------------------------------------
+static unsigned grid_for(long long total) {
+    long long g = (total + 255) / 256;
+    if (g > 148ll * 64) g = 148ll * 64;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+static bool build_generic(Builder &B) {
+    Plan *P = B.P;
+    const int rank = P->rank;
+    const long long *n = P->n;
+    const size_t ce = P->prec ? 16 : 8;
+    long long total_in = P->batch;
+    for (int d = 0; d < rank; ++d) total_in *= n[d];
+    P->work_bytes = (size_t)total_in * ce;
+    P->work[0] = B.alloc(P->work_bytes);
+    P->work[1] = B.alloc(P->work_bytes);
+    if (!P->work[0] || !P->work[1]) return false;
+    P->generic = true;
+    P->inplace_ok = true;
+
+    Launch g;
+    g.kind = Launch::GEN_GATHER;
+    g.real_in = P->real;
+    g.lay.nd = rank + 1;
+    g.lay.n[0] = P->batch;
+    g.lay.stride[0] = P->in_stride[0];
+    for (int d = 0; d < rank; ++d) { g.lay.n[d + 1] = n[d]; g.lay.stride[d + 1] = P->in_stride[d + 1]; }
+    g.total = total_in;
+    g.src = BUF_IN;
+    g.dst = BUF_WORK0;
+    g.grid = grid_for(total_in);
+    g.algo_bytes = (unsigned long long)total_in * (P->elt_in() + ce);
+    g.desc = "generic gather (user layout -> packed complex)";
+    P->launches.push_back(g);
+
+    int cur = BUF_WORK0;
+    long long dims[3];
+    for (int d = 0; d < rank; ++d) dims[d] = n[d];
+    for (int axis = rank - 1; axis >= 0; --axis) {
+        const int L = (int)dims[axis];
+        long long outer = P->batch, inner = 1;
+        for (int d = 0; d < axis; ++d) outer *= dims[d];
+        for (int d = axis + 1; d < rank; ++d) inner *= dims[d];
+        if (L > 1) {
+            const double2 *tw = (const double2 *)B.table(L, L, true);
+            int rem = L, Ns = 1;
+            for (int p = 2; rem > 1; ++p) {
+                if ((long long)p * p > rem) p = rem;
+                while (rem % p == 0) {
+                    Launch s;
+                    s.kind = Launch::GEN_STAGE;
+                    s.outer = outer;
+                    s.inner = inner;
+                    s.L = L;
+                    s.p = p;
+                    s.Ns = Ns;
+                    s.gtw = tw;
+                    s.src = cur;
+                    s.dst = (cur == BUF_WORK0) ? BUF_WORK1 : BUF_WORK0;
+                    s.total = outer * L * inner;
+                    s.grid = grid_for(s.total);
+                    s.algo_bytes = (unsigned long long)s.total * ce * 2ull;
+                    char buf[160];
+                    snprintf(buf, sizeof buf, "generic stage axis=%d L=%d radix=%d Ns=%d lines=%lld", axis, L, p, Ns,
+                             outer * inner);
+                    s.desc = buf;
+                    P->launches.push_back(s);
+                    cur = s.dst;
+                    Ns *= p;
+                    rem /= p;
+                }
+            }
+        }
+        if (P->real && axis == rank - 1) {
+            Launch t;
+            t.kind = Launch::GEN_TRUNC;
+            t.outer = outer;  // lines (inner == 1 on the last axis)
+            t.L = L;
+            t.Lc = L / 2 + 1;
+            t.src = cur;
+            t.dst = (cur == BUF_WORK0) ? BUF_WORK1 : BUF_WORK0;
+            t.total = outer * t.Lc;
+            t.grid = grid_for(t.total);
+            t.algo_bytes = (unsigned long long)t.total * ce * 2ull;
+            t.desc = "generic truncate to n/2+1";
+            P->launches.push_back(t);
+            cur = t.dst;
+            dims[axis] = t.Lc;
+        }
+    }
+    Launch s;
+    s.kind = Launch::GEN_SCATTER;
+    s.lay.nd = rank + 1;
+    s.lay.n[0] = P->batch;
+    s.lay.stride[0] = P->out_stride[0];
+    long long total_out = P->batch;
+    for (int d = 0; d < rank; ++d) { s.lay.n[d + 1] = dims[d]; s.lay.stride[d + 1] = P->out_stride[d + 1]; total_out *= dims[d]; }
+    s.total = total_out;
+    s.src = cur;
+    s.dst = BUF_OUT;
+    s.grid = grid_for(total_out);
+    s.algo_bytes = (unsigned long long)total_out * ce * 2ull;
+    s.desc = "generic scatter (packed complex -> user layout)";
+    P->launches.push_back(s);
+    return B.err == FFTB200_SUCCESS;
+}
+
+int create_plan(Plan **out, int rank, const long long *n, int batch, const long long *in_stride,
+                       const long long *out_stride, fftb200_type type, bool force_generic) {
+    std::unique_ptr<Plan> P(new Plan);
+    if (cudaGetDevice(&P->device) != cudaSuccess) { cudaGetLastError(); return FFTB200_SETUP_FAILED; }
+    P->type = type;
+    P->prec = (type == FFTB200_Z2Z || type == FFTB200_D2Z || type == FFTB200_Z2D) ? 1 : 0;
+    P->real = (type == FFTB200_R2C || type == FFTB200_D2Z);
+    P->c2r = (type == FFTB200_C2R || type == FFTB200_Z2D);
+    P->rank = rank;
+    P->batch = batch;
+    for (int d = 0; d < rank; ++d) P->n[d] = n[d];
+    for (int d = 0; d <= rank; ++d) { P->in_stride[d] = in_stride[d]; P->out_stride[d] = out_stride[d]; }
+    {
+        long long li = 0, lo = 0, dense = 1;
+        for (int d = 0; d < rank; ++d) {
+            const long long no = (P->real && d == rank - 1) ? n[d] / 2 + 1 : n[d];
+            const long long ni = (P->c2r && d == rank - 1) ? n[d] / 2 + 1 : n[d];
+            li += (ni - 1) * in_stride[d + 1];
+            lo += (no - 1) * out_stride[d + 1];
+            dense *= no;
+        }
+        li += (long long)(batch - 1) * in_stride[0];
+        lo += (long long)(batch - 1) * out_stride[0];
+        dense *= batch;
+        P->span_in = (size_t)(li + 1) * P->elt_in();
+        P->span_out = (size_t)(lo + 1) * P->elt_out();
+        P->out_dense = (lo + 1 == dense);
+    }
+    Builder B;
+    B.P = P.get();
+    bool ok = false;
+    if (P->c2r) {
+        if (!build_c2r(B)) {
+            free_plan_resources(P.get());
+            return B.err != FFTB200_SUCCESS ? B.err : FFTB200_UNSUPPORTED;  // power-of-two, unit-stride layouts only
+        }
+        *out = P.release();
+        return FFTB200_SUCCESS;
+    }
+    if (!force_generic) {
+        ok = build_fast(B);
+        if (!ok) {
+            // discard partial fast plan
+            P->launches.clear();
+            for (void *d : P->dev_allocs) cudaFree(d);
+            P->dev_allocs.clear();
+            B.cache.clear();
+            P->work[0] = P->work[1] = nullptr;
+            P->work_bytes = 0;
+            if (B.err != FFTB200_SUCCESS) return B.err;
+        }
+    }
+    if (!ok) ok = build_generic(B);
+    if (!ok) {
+        free_plan_resources(P.get());
+        return B.err != FFTB200_SUCCESS ? B.err : FFTB200_UNSUPPORTED;
+    }
+    *out = P.release();
+    return FFTB200_SUCCESS;
+}
+
+}  // namespace fftb200

@@ -1,0 +1,256 @@
+// plan_exec.cu — runs a plan's launches (host-memory staging, per-launch profiling events), owns the handle table.
+// No CPU fallback exists: if a kernel cannot be launched the call returns an error code.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "plan_internal.h"
+
+namespace fftb200 {
+
+// one launch of a tile pass; cluster kernels go through cudaLaunchKernelEx with the cluster dimension
+cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st, const TileParams &tp, bool bulk) {
+    if (bulk && ki->fn_bulk) {
+        ki->fn_bulk<<<grid, ki->threads, ki->smem_bytes, st>>>(tp);
+        return cudaGetLastError();
+    }
+    if (tp.ticket) {
+        const cudaError_t e = cudaMemsetAsync(tp.ticket, 0, sizeof(unsigned), st);
+        if (e != cudaSuccess) return e;
+    }
+    if (ki->cluster <= 1) {
+        ki->fn<<<grid, ki->threads, ki->smem_bytes, st>>>(tp);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid / ki->cluster * ki->cluster, 1, 1);
+    cfg.blockDim = dim3(ki->threads, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)ki->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)ki->cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, ki->fn, tp);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+void free_plan_resources(Plan *p) {
+    DeviceGuard g(p->device);
+    slab_free(p);
+    for (void *d : p->dev_allocs) cudaFree(d);
+    p->dev_allocs.clear();
+    for (auto &row : p->prof_rows)
+        for (cudaEvent_t e : row) cudaEventDestroy(e);
+    p->prof_rows.clear();
+    p->prof_used = 0;
+    if (p->stage_in) cudaFree(p->stage_in);
+    if (p->stage_out) cudaFree(p->stage_out);
+    p->stage_in = p->stage_out = nullptr;
+    if (p->fallback) free_plan_resources(p->fallback.get());
+}
+
+// ------------------------------------------------------------------------------------------
+// handle table: handle = (generation << 32) | (slot + 1); never a raw pointer, so a stale or
+// zero-filled plan region (src/fft.rg:523-531) cannot crash the library
+// ------------------------------------------------------------------------------------------
+static std::mutex g_mu;
+static std::vector<std::pair<unsigned, Plan *>> g_slots;  // (generation, plan)
+
+fftb200_handle register_plan(Plan *p) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (size_t i = 0; i < g_slots.size(); ++i)
+        if (!g_slots[i].second) {
+            g_slots[i].first++;
+            g_slots[i].second = p;
+            return ((fftb200_handle)g_slots[i].first << 32) | (fftb200_handle)(i + 1);
+        }
+    g_slots.push_back({1u, p});
+    return ((fftb200_handle)1 << 32) | (fftb200_handle)g_slots.size();
+}
+
+Plan *lookup_plan(fftb200_handle h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const size_t slot = (size_t)(h & 0xffffffffull);
+    const unsigned gen = (unsigned)(h >> 32);
+    if (slot == 0 || slot > g_slots.size()) return nullptr;
+    if (g_slots[slot - 1].first != gen) return nullptr;
+    return g_slots[slot - 1].second;
+}
+
+Plan *unregister_plan(fftb200_handle h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const size_t slot = (size_t)(h & 0xffffffffull);
+    const unsigned gen = (unsigned)(h >> 32);
+    if (slot == 0 || slot > g_slots.size()) return nullptr;
+    if (g_slots[slot - 1].first != gen) return nullptr;
+    Plan *p = g_slots[slot - 1].second;
+    g_slots[slot - 1].second = nullptr;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// execution
+// ------------------------------------------------------------------------------------------
+template <typename T> static cudaError_t launch_generic(const Launch &ln, const void *src, void *dst, int inverse,
+                                                        cudaStream_t st) {
+    using C = cplx<T>;
+    switch (ln.kind) {
+        case Launch::GEN_GATHER:
+            if (ln.real_in)
+                gen_gather_kernel<T, true><<<ln.grid, 256, 0, st>>>(src, (C *)dst, ln.lay, ln.total, 0);
+            else
+                gen_gather_kernel<T, false><<<ln.grid, 256, 0, st>>>(src, (C *)dst, ln.lay, ln.total, inverse);
+            break;
+        case Launch::GEN_STAGE:
+            gen_stage_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.gtw, ln.outer, ln.L, ln.inner,
+                                                         ln.p, ln.Ns);
+            break;
+        case Launch::GEN_TRUNC:
+            gen_truncate_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.outer, ln.L, ln.Lc);
+            break;
+        case Launch::GEN_SCATTER:
+            gen_scatter_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.lay, ln.total, inverse);
+            break;
+        default: break;
+    }
+    return cudaGetLastError();
+}
+
+
+static int exec_fallback(Plan *P, const void *in, void *out, int direction);
+
+// true when the kernels cannot (or should not) read the pointer directly: pageable host memory is
+// not device-accessible at all, pinned / zero-copy host memory would be re-streamed over PCIe by
+// every pass
+static bool is_host_memory(const void *ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeUnregistered;
+}
+
+static const size_t PROF_MAX_EXECS = 256;
+
+static int run_launches(Plan *P, const void *in, void *out, int inverse) {
+    const size_t nl = P->launches.size();
+    std::vector<cudaEvent_t> *row = nullptr;
+    if (P->profiling && P->prof_used < PROF_MAX_EXECS) {
+        if (P->prof_rows.size() <= P->prof_used) {
+            std::vector<cudaEvent_t> r(nl + 1, nullptr);
+            for (size_t i = 0; i <= nl; ++i)
+                if (cudaEventCreate(&r[i]) != cudaSuccess) return FFTB200_INTERNAL_ERROR;
+            P->prof_rows.push_back(r);
+        }
+        row = &P->prof_rows[P->prof_used++];
+        cudaEventRecord((*row)[0], P->stream);
+    }
+    for (size_t i = 0; i < nl; ++i) {
+        const Launch &ln = P->launches[i];
+        const void *bufs_src[4] = {in, out, P->work[0], P->work[1]};
+        void *bufs_dst[4] = {nullptr, out, P->work[0], P->work[1]};
+        const void *src = bufs_src[ln.src];
+        void *dst = bufs_dst[ln.dst];
+        cudaError_t ce;
+        if (ln.kind == Launch::TILE) {
+            TileParams tp = ln.tp;
+            tp.in = src;
+            tp.out = dst;
+            tp.inverse = inverse;
+            tp.ticket = ln.ticket;
+            ce = launch_tile(ln.ki, ln.grid, P->stream, tp, ln.bulk);
+        } else if (ln.kind == Launch::FUSED) {
+            FusedParams fp;
+            fp.a = ln.tp;
+            fp.a.in = src;
+            fp.a.out = dst;
+            fp.a.inverse = inverse;
+            fp.b = ln.tp_b;
+            fp.b.in = dst;
+            fp.b.out = dst;
+            fp.b.inverse = inverse;
+            fp.counters = ln.counters;
+            fp.tiles_a = ln.tiles_a;
+            fp.tiles_b = ln.tiles_b;
+            fp.n_groups = ln.n_groups;
+            fp.lag = ln.lag;
+            ce = cudaMemsetAsync(ln.counters, 0, sizeof(unsigned) * (size_t)(1 + ln.n_groups), P->stream);
+            if (ce == cudaSuccess) {
+                ln.fk->fn<<<ln.grid, ln.fk->threads, ln.fk->smem_bytes, P->stream>>>(fp);
+                ce = cudaGetLastError();
+            }
+        } else {
+            ce = P->prec ? launch_generic<double>(ln, src, dst, inverse, P->stream)
+                         : launch_generic<float>(ln, src, dst, inverse, P->stream);
+        }
+        if (ce != cudaSuccess) return FFTB200_EXEC_FAILED;
+        if (row) cudaEventRecord((*row)[i + 1], P->stream);
+    }
+    return FFTB200_SUCCESS;
+}
+
+int exec_plan(Plan *P, const void *in, void *out, int direction) {
+    if (!in || !out) return FFTB200_INVALID_VALUE;
+    if (direction != FFTB200_FORWARD && direction != FFTB200_INVERSE) return FFTB200_INVALID_VALUE;
+    if (P->real && direction != FFTB200_FORWARD) return FFTB200_INVALID_VALUE;
+    if (P->c2r && direction != FFTB200_INVERSE) return FFTB200_INVALID_VALUE;
+    if (in == out && !P->inplace_ok) return FFTB200_INVALID_VALUE;
+    const bool host_in = is_host_memory(in), host_out = is_host_memory(out);
+    if (!P->generic && !(host_in && host_out)) {
+        const size_t a_in = P->real ? 2 * P->elt_in() : P->elt_in();
+        const size_t a_out = P->c2r ? 2 * P->elt_out() : P->elt_out();
+        if ((!host_in && ((uintptr_t)in % a_in)) || (!host_out && ((uintptr_t)out % a_out))) {
+            if (P->c2r) return FFTB200_INVALID_VALUE;  // no generic path for inverse real transforms
+            return exec_fallback(P, in, out, direction);
+        }
+    }
+    DeviceGuard g(P->device);
+    std::lock_guard<std::mutex> lk(P->mu);
+    const int inverse = (direction == FFTB200_INVERSE) ? 1 : 0;
+    const void *din = in;
+    void *dout = out;
+    if (host_in) {
+        if (!P->stage_in && cudaMalloc(&P->stage_in, P->span_in) != cudaSuccess) { cudaGetLastError(); return FFTB200_ALLOC_FAILED; }
+        if (cudaMemcpyAsync(P->stage_in, in, P->span_in, cudaMemcpyHostToDevice, P->stream) != cudaSuccess) {
+            cudaGetLastError();
+            return FFTB200_EXEC_FAILED;
+        }
+        din = P->stage_in;
+    }
+    if (host_out) {
+        if (!P->stage_out && cudaMalloc(&P->stage_out, P->span_out) != cudaSuccess) { cudaGetLastError(); return FFTB200_ALLOC_FAILED; }
+        // padding between rows / batches must survive the round trip
+        if (!P->out_dense &&
+            cudaMemcpyAsync(P->stage_out, out, P->span_out, cudaMemcpyHostToDevice, P->stream) != cudaSuccess) {
+            cudaGetLastError();
+            return FFTB200_EXEC_FAILED;
+        }
+        dout = P->stage_out;
+    }
+    const int rc = run_launches(P, din, dout, inverse);
+    if (rc != FFTB200_SUCCESS) return rc;
+    if (host_out && cudaMemcpyAsync(out, P->stage_out, P->span_out, cudaMemcpyDeviceToHost, P->stream) != cudaSuccess) {
+        cudaGetLastError();
+        return FFTB200_EXEC_FAILED;
+    }
+    return FFTB200_SUCCESS;
+}
+
+static int exec_fallback(Plan *P, const void *in, void *out, int direction) {
+    {
+        std::lock_guard<std::mutex> lk(P->mu);
+        if (!P->fallback) {
+            DeviceGuard g(P->device);
+            Plan *fb = nullptr;
+            const int rc = create_plan(&fb, P->rank, P->n, P->batch, P->in_stride, P->out_stride, P->type, true);
+            if (rc != FFTB200_SUCCESS) return rc;
+            P->fallback.reset(fb);
+        }
+        P->fallback->stream = P->stream;
+    }
+    return exec_plan(P->fallback.get(), in, out, direction);
+}
+
+}  // namespace fftb200

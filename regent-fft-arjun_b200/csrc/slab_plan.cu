@@ -1,5 +1,4 @@
-// slab_plan.inl — multi-GPU slab decomposition of 3-D transforms (included by fft_b200.cu inside
-// namespace fftb200; it uses the plan builder's internals).
+// slab_plan.cu — multi-GPU slab decomposition of 3-D (and 2-D complex) transforms.
 //
 // No reference counterpart in src/fft.rg (its "distrib" path runs independent shard FFTs,
 // src/fft.rg:513-537; README.md:117-119 lists a distributed transform as future work).  The scheme is
@@ -25,6 +24,14 @@
 // p2p mode pipelines passes 2 and 3 over J chunks of the contiguous index i: chunk j of pass 3 starts
 // as soon as every rank has signalled chunk j of pass 2 (flags written into each peer's exchange area),
 // so the z-axis pass hides under the NVLink transfer of the following chunks.
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "plan_internal.h"
+
+namespace fftb200 {
 
 struct SlabState {
     int rank = 0, G = 1, J = 1;
@@ -87,7 +94,7 @@ __global__ void slab_wait_kernel(const unsigned long long *flags, int G, int kin
     __threadfence_system();
 }
 
-static void slab_free(Plan *P) {
+void slab_free(Plan *P) {
     SlabState *S = P->slab;
     if (!S) return;
     for (int d = 0; d < S->G; ++d)
@@ -119,13 +126,8 @@ static int slab_launch(Plan *P, int idx, const void *src, void *dst, void *const
     return launch_tile(ln.ki, ln.grid, st, tp) == cudaSuccess ? FFTB200_SUCCESS : FFTB200_EXEC_FAILED;
 }
 
-// benchmarking override only (SURVEY.md §5 "config / flags"): FFTB200_SLAB_P2_CTAS = CTAs the exchange pass may use
-static int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
 
-static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, int chunks) {
+int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, int chunks) {
     if (G < 1 || G > MAX_PEERS || rank < 0 || rank >= G) return FFTB200_INVALID_VALUE;
     for (int d = 0; d < 3; ++d)
         if (n[d] < 2 || !is_pow2(n[d])) return FFTB200_INVALID_SIZE;
@@ -215,7 +217,7 @@ static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, in
         // The exchange pass is NVLink-bound, not SM-bound: when it is pipelined against the z-axis pass
         // keep it persistent on a bounded number of CTAs so that the HBM-bound pass finds free SMs.
         if (G > 1 && S->J > 1) {
-            const unsigned cap = (unsigned)env_int("FFTB200_SLAB_P2_CTAS", 148);
+            const unsigned cap = (unsigned)env_int_or("FFTB200_SLAB_P2_CTAS", 148);
             // static tile assignment on purpose: with dynamic tickets (TileParams::ticket) every capped CTA stays
             // resident until the chunk ends and the overlapped pass starves (2 x B200, 512^3: 1.61 vs 1.40 ms)
             if (cap > 0 && ln.grid > cap) ln.grid = std::max(1u, cap / ln.ki->cluster) * ln.ki->cluster;
@@ -256,7 +258,7 @@ static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, in
     // lies in chunk c of any rank) start as soon as chunk c has arrived from every rank: it hides under the
     // NVLink transfer of the following chunks, and only the z-axis pass is left after the exchange.
     if (!P->real) {
-        int want = env_int("FFTB200_SLAB_PLANE_CHUNKS", 0);
+        int want = env_int_or("FFTB200_SLAB_PLANE_CHUNKS", 0);
         if (want <= 0) want = (G > 1) ? 4 : 1;
         long long Jp = 1;
         while (Jp * 2 <= want && S->n0l % (Jp * 2) == 0) Jp *= 2;
@@ -273,7 +275,7 @@ static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, in
             ln.out_off = ((long long)rank * S->n0l + (long long)c * pc) * S->n2p;
             set_peer(ln);
             if (G > 1 && S->Jp > 1 && ln.ki->cluster == 1) {  // (a capped cluster pass pays a cluster barrier per tile)
-                const unsigned cap = (unsigned)env_int("FFTB200_SLAB_P2_CTAS", 148);
+                const unsigned cap = (unsigned)env_int_or("FFTB200_SLAB_P2_CTAS", 148);
                 if (cap > 0 && ln.grid > cap) ln.grid = cap;  // static assignment, see the R2C pipeline above
             }
             S->l_y.push_back((int)P->launches.size() - 1);
@@ -308,7 +310,7 @@ static int slab_create(Plan **out, const int *n, fftb200_type type, int rank, in
     return FFTB200_SUCCESS;
 }
 
-static int slab_create_2d(Plan **out, const int *n, fftb200_type type, int rank, int G) {
+int slab_create_2d(Plan **out, const int *n, fftb200_type type, int rank, int G) {
     if (G < 1 || G > MAX_PEERS || rank < 0 || rank >= G) return FFTB200_INVALID_VALUE;
     for (int d = 0; d < 2; ++d)
         if (n[d] < 2 || !is_pow2(n[d])) return FFTB200_INVALID_SIZE;
@@ -376,7 +378,7 @@ static unsigned long long *slab_flags(SlabState *S, int d) {
 }
 
 // fused exchange: every rank calls this once per transform (collective)
-static int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
+int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
     SlabState *S = P->slab;
     if (!S->connected) return FFTB200_INVALID_PLAN;
     DeviceGuard g(P->device);
@@ -460,7 +462,7 @@ static int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
     return cudaGetLastError() == cudaSuccess ? FFTB200_SUCCESS : FFTB200_EXEC_FAILED;
 }
 
-static int slab_exec_pre(Plan *P, const void *in, void *send, int inverse) {
+int slab_exec_pre(Plan *P, const void *in, void *send, int inverse) {
     SlabState *S = P->slab;
     DeviceGuard g(P->device);
     std::lock_guard<std::mutex> lk(P->mu);
@@ -472,9 +474,92 @@ static int slab_exec_pre(Plan *P, const void *in, void *send, int inverse) {
     return slab_launch(P, S->l_pre2, S->tmp, nullptr, blocks, inverse, P->stream);
 }
 
-static int slab_exec_post(Plan *P, const void *recv, void *out, int inverse) {
+int slab_exec_post(Plan *P, const void *recv, void *out, int inverse) {
     SlabState *S = P->slab;
     DeviceGuard g(P->device);
     std::lock_guard<std::mutex> lk(P->mu);
     return slab_launch(P, S->l_post3, recv, out, nullptr, inverse, P->stream);
 }
+
+// ---- accessors used by the C ABI (abi.cu) ---------------------------------------------------------------
+int slab_get_ipc_handle(Plan *P, void *handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(P->device);
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, P->slab->area) != cudaSuccess) { cudaGetLastError(); return FFTB200_SETUP_FAILED; }
+    memcpy(handle64, &h, 64);
+    return FFTB200_SUCCESS;
+}
+
+int slab_connect_ipc(Plan *P, const void *handles) {
+    SlabState *S = P->slab;
+    DeviceGuard g(P->device);
+    std::lock_guard<std::mutex> lk(P->mu);
+    for (int d = 0; d < S->G; ++d) {
+        if (d == S->rank || S->peer_mapped[d]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)d, 64);
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            return FFTB200_SETUP_FAILED;
+        }
+        S->peer_area[d] = ptr;
+        S->peer_mapped[d] = true;
+    }
+    S->connected = true;
+    return FFTB200_SUCCESS;
+}
+
+int slab_get_area(Plan *P, void **area, unsigned long long *bytes) {
+    *area = P->slab->area;
+    if (bytes) *bytes = P->slab->area_bytes;
+    return FFTB200_SUCCESS;
+}
+
+int slab_connect_ptrs(Plan *P, void *const *areas) {
+    SlabState *S = P->slab;
+    DeviceGuard g(P->device);
+    std::lock_guard<std::mutex> lk(P->mu);
+    for (int d = 0; d < S->G; ++d) {
+        if (d == S->rank) continue;
+        if (!areas[d]) return FFTB200_INVALID_VALUE;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, areas[d]) != cudaSuccess) { cudaGetLastError(); return FFTB200_INVALID_VALUE; }
+        if (a.device != P->device) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return FFTB200_SETUP_FAILED; }
+            cudaGetLastError();
+        }
+        S->peer_area[d] = areas[d];
+    }
+    S->connected = true;
+    return FFTB200_SUCCESS;
+}
+
+int slab_set_timing(Plan *P, int on) {
+    std::lock_guard<std::mutex> lk(P->mu);
+    P->slab->timing = on != 0;
+    return FFTB200_SUCCESS;
+}
+
+// ms[0] = first phase, ms[1] = pass(es) with the exchange, ms[2] = remaining local work
+int slab_get_phase_ms(Plan *P, float *ms) {
+    SlabState *S = P->slab;
+    std::lock_guard<std::mutex> lk(P->mu);
+    DeviceGuard g(P->device);
+    if (cudaEventSynchronize(S->ev_t[3]) != cudaSuccess) { cudaGetLastError(); return FFTB200_INVALID_VALUE; }
+    for (int i = 0; i < 3; ++i)
+        if (cudaEventElapsedTime(&ms[i], S->ev_t[i], S->ev_t[i + 1]) != cudaSuccess) { cudaGetLastError(); return FFTB200_INVALID_VALUE; }
+    return FFTB200_SUCCESS;
+}
+
+// kernels one fused slab exec issues: pass 1, J x (pass 2 + pass 3), hand-shake kernels
+int slab_launches_per_exec(const Plan *P) {
+    const SlabState *S = P->slab;
+    if (S->two_d) return 2 + (S->G > 1 ? 4 : 0);
+    const int J = P->real ? S->J : S->Jp;
+    return 1 + 2 * J + (S->G > 1 ? 2 + 2 * J : 0);
+}
+
+}  // namespace fftb200

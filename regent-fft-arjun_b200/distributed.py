@@ -2,7 +2,7 @@
 
 The reference has no distributed transform (README.md:117-119 "Future Developments"; its
 `make_plan_distrib`, src/fft.rg:513-537, runs independent shard FFTs).  This module is the host side
-of libfft_b200's slab plans (include/fft_b200.h, csrc/slab_plan.inl), laid out like the vendored
+of libfft_b200's slab plans (include/fft_b200.h, csrc/slab_plan.cu), laid out like the vendored
 FFTW-MPI (fftw-3.3.8/mpi/dft-rank-geq2.c:40-59, doc/mpi.texi:259-270, 443-466):
 
     rank r holds  in  [n0/G][n1][n2]     (slab r of dimension 0)
@@ -33,7 +33,7 @@ def slab_shapes(shape, world: int, real: bool):
 
 
 def slab_chunks(n2c: int, chunks: int) -> int:
-    """number of pipeline chunks the library makes of the contiguous index (csrc/slab_plan.inl)"""
+    """number of pipeline chunks the library makes of the contiguous index (csrc/slab_plan.cu)"""
     cw = -(-n2c // max(1, chunks))
     cw = -(-cw // 16) * 16
     return -(-n2c // cw)
