@@ -124,9 +124,21 @@ template <typename T> __device__ __forceinline__ cplx<T> ld_cplx(const cplx<T> *
 #ifndef FFTB200_STREAMING
 #define FFTB200_STREAMING 0
 #endif
+__device__ __forceinline__ double2 ld_noalloc(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ld_noalloc(const float2 *p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
 template <typename T> __device__ __forceinline__ cplx<T> ld_data(const cplx<T> *p) {
-#if FFTB200_STREAMING
+#if FFTB200_STREAMING == 1
     return __ldcs(p);
+#elif FFTB200_STREAMING == 2
+    return ld_noalloc(p);  // keep L1 for the twiddle tables
 #else
     return __ldg(p);
 #endif

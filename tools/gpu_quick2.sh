@@ -1,4 +1,2 @@
 #!/bin/bash
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --no-cpu-baseline | cut -c1-200
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29552 bench.py --gpus 2 | grep "^{" | cut -c1-200
+python tools/ab_probe.py $PWD/regent-fft-arjun_b200/libfft_b200.so $PWD/tools/altlibs/lib_noalloc.so
