@@ -545,7 +545,7 @@ def test_native_library_is_the_one_running(fft, L):
     assert "NEEDED" in needed and "cufft" not in needed.lower() and "nccl" not in needed.lower(), needed
     h = L.plan_many(3, [512, 512, 512], None, 0, 0, None, 0, 0, L.Z2Z, 1)
     nl = L.launch_count(h)
-    assert nl in (2, 3) and L.work_size(h) == 0
+    assert nl in (2, 3) and L.work_size(h) in (0, 512 ** 3 * 16)     # blocked intermediate layout uses one work buffer
     total = sum(L.launch_bytes(h, i) for i in range(nl))
     # compulsory HBM bytes: one read + one write of 512^3 complex64 per launch (a fused launch covers two
     # axis passes of SURVEY.md §8d's pass model with the traffic of one)
@@ -771,3 +771,32 @@ def test_inverse_real_transforms(L, oracle):
     hbad = ctypes.c_ulonglong(0)
     n3 = (ctypes.c_int * 1)(12)
     assert lib.fftb200_plan_many(ctypes.byref(hbad), 1, n3, None, 0, 0, None, 0, 0, L.Z2D, 1) == L.UNSUPPORTED   # not 2^k
+
+
+def test_blocked_intermediate_layout_matches_in_place_plan(L, oracle, monkeypatch):
+    """3-D complex plans with a far slowest-axis stride route the middle pass through a blocked work buffer; the
+    result is bit-identical to the in-place three-pass plan (FFTB200_ZBLOCK=0), also in place and backward."""
+    for kind, shape in [("z2z", (128, 128, 128)), ("c2c", (128, 256, 256)), ("z2z", (256, 512, 64)), ("z2z", (128, 128, 512)),
+                        ("c2c", (512, 128, 256))]:
+        ftype, dt_in, _ = _kinds(L)[kind]
+        x = torch.from_numpy(oracle.synth(shape, dt_in, 1400)).cuda()
+        outs, descs, works = [], [], []
+        for z in ("1", "0"):
+            monkeypatch.setenv("FFTB200_ZBLOCK", z)
+            h = L.plan_many(3, list(shape), None, 0, 0, None, 0, 0, ftype, 1)
+            y = torch.zeros_like(x)
+            L.execute(h, ftype, x.data_ptr(), y.data_ptr())
+            xi = x.clone()
+            L.execute(h, ftype, xi.data_ptr(), xi.data_ptr())                 # in place
+            b = torch.zeros_like(x)
+            L.execute(h, ftype, y.data_ptr(), b.data_ptr(), +1)               # backward
+            torch.cuda.synchronize()
+            descs.append(L.describe(h)); works.append(L.work_size(h))
+            L.destroy(h)
+            assert torch.equal(xi, y), (kind, shape, "in place", z)
+            outs.append((y, b))
+        assert "blocked" in descs[0] and "blocked" not in descs[1], descs
+        assert works[0] == x.numel() * x.element_size() and works[1] == 0
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (kind, shape)
+        want = cpu_fft(oracle, kind, x.cpu().numpy(), shape)
+        assert oracle.rel_l2(outs[0][0].cpu().numpy(), want) <= oracle.tolerance(int(np.prod(shape)), kind == "c2c")
