@@ -41,7 +41,9 @@
  *   - handles are plain 64-bit integers (0 = null) that survive being memcpy'd inside the plan
  *     region (src/fft.rg:48-65); destroy(0) is a no-op and destroy needs no current device
  *     (src/fft.rg:523-531, 624-645).
- *   - thread-safe across plans (Legion runs one task per GPU processor concurrently).
+ *   - thread-safe across plans (Legion runs one task per GPU processor concurrently).  One plan is one
+ *     execution context, as with cuFFT: it owns twiddle tables and, for some shapes, a work buffer (four/six-step
+ *     1-D, blocked 3-D intermediate, host staging), so execs of the SAME plan must be ordered on one stream.
  *
  * There is no CPU fallback: every exec runs hand-written sm_100a kernels or fails.
  */
