@@ -61,7 +61,8 @@ int fftb200_plan_many(fftb200_handle *plan, int rank, const int *n, const int *i
 }
 
 int fftb200_set_stream(fftb200_handle plan, void *cuda_stream) {
-    Plan *P = lookup_plan(plan);
+    const std::shared_ptr<Plan> hold = lookup_plan(plan);
+    Plan *P = hold.get();
     if (!P) return FFTB200_INVALID_PLAN;
     std::lock_guard<std::mutex> lk(P->mu);
     P->stream = (cudaStream_t)cuda_stream;
@@ -69,7 +70,8 @@ int fftb200_set_stream(fftb200_handle plan, void *cuda_stream) {
 }
 
 static int exec_typed(fftb200_handle plan, const void *in, void *out, int direction, fftb200_type want) {
-    Plan *P = lookup_plan(plan);
+    const std::shared_ptr<Plan> hold = lookup_plan(plan);
+    Plan *P = hold.get();
     if (!P) return FFTB200_INVALID_PLAN;
     if (P->type != want) return FFTB200_INVALID_TYPE;
     if (P->slab) return FFTB200_INVALID_PLAN;  // slab plans run through fftb200_slab_exec*
@@ -97,22 +99,22 @@ int fftb200_exec_z2d(fftb200_handle plan, const void *in, void *out) {
 
 int fftb200_destroy(fftb200_handle plan) {
     if (plan == 0) return FFTB200_SUCCESS;  // zero-filled plan regions (src/fft.rg:523-531)
-    Plan *P = unregister_plan(plan);
-    if (!P) return FFTB200_INVALID_PLAN;
-    free_plan_resources(P);
-    delete P;
-    return FFTB200_SUCCESS;
+    const std::shared_ptr<Plan> hold = unregister_plan(plan);
+    if (!hold) return FFTB200_INVALID_PLAN;
+    return FFTB200_SUCCESS;  // resources are released when the last call still using the plan returns (~Plan)
 }
 
 int fftb200_get_work_size(fftb200_handle plan, unsigned long long *bytes) {
-    Plan *P = lookup_plan(plan);
+    const std::shared_ptr<Plan> hold = lookup_plan(plan);
+    Plan *P = hold.get();
     if (!P || !bytes) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     *bytes = (unsigned long long)P->work_bytes * ((P->work[0] ? 1 : 0) + (P->work[1] ? 1 : 0));
     return FFTB200_SUCCESS;
 }
 
 int fftb200_get_launch_count(fftb200_handle plan, int *launches) {
-    Plan *P = lookup_plan(plan);
+    const std::shared_ptr<Plan> hold = lookup_plan(plan);
+    Plan *P = hold.get();
     if (!P || !launches) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     *launches = (int)P->launches.size();
     if (P->slab) *launches = slab_launches_per_exec(P);
@@ -120,7 +122,8 @@ int fftb200_get_launch_count(fftb200_handle plan, int *launches) {
 }
 
 int fftb200_describe(fftb200_handle plan, char *buf, int buflen) {
-    Plan *P = lookup_plan(plan);
+    const std::shared_ptr<Plan> hold = lookup_plan(plan);
+    Plan *P = hold.get();
     if (!P || !buf || buflen < 1) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     std::string s;
     for (const Launch &l : P->launches) { s += l.desc; s += "\n"; }
@@ -129,7 +132,8 @@ int fftb200_describe(fftb200_handle plan, char *buf, int buflen) {
 }
 
 int fftb200_get_launch_bytes(fftb200_handle plan, int i, unsigned long long *bytes) {
-    Plan *P = lookup_plan(plan);
+    const std::shared_ptr<Plan> hold = lookup_plan(plan);
+    Plan *P = hold.get();
     if (!P || !bytes) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     if (i < 0 || i >= (int)P->launches.size()) return FFTB200_INVALID_VALUE;
     *bytes = P->launches[i].algo_bytes;
@@ -137,7 +141,8 @@ int fftb200_get_launch_bytes(fftb200_handle plan, int i, unsigned long long *byt
 }
 
 int fftb200_set_profiling(fftb200_handle plan, int on) {
-    Plan *P = lookup_plan(plan);
+    const std::shared_ptr<Plan> hold = lookup_plan(plan);
+    Plan *P = hold.get();
     if (!P) return FFTB200_INVALID_PLAN;
     std::lock_guard<std::mutex> lk(P->mu);
     P->profiling = on != 0;
@@ -147,7 +152,8 @@ int fftb200_set_profiling(fftb200_handle plan, int on) {
 
 // mean duration of launch i over the execs recorded since profiling was switched on
 int fftb200_get_launch_ms(fftb200_handle plan, int i, float *ms) {
-    Plan *P = lookup_plan(plan);
+    const std::shared_ptr<Plan> hold = lookup_plan(plan);
+    Plan *P = hold.get();
     if (!P || !ms) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     std::lock_guard<std::mutex> lk(P->mu);
     if (i < 0 || i >= (int)P->launches.size() || P->prof_used == 0) return FFTB200_INVALID_VALUE;
@@ -164,9 +170,9 @@ int fftb200_get_launch_ms(fftb200_handle plan, int i, float *ms) {
 }
 
 // ---- multi-GPU slab transforms ------------------------------------------------------------
-static Plan *lookup_slab(fftb200_handle plan) {
-    Plan *P = lookup_plan(plan);
-    return (P && P->slab) ? P : nullptr;
+static std::shared_ptr<Plan> lookup_slab(fftb200_handle plan) {
+    std::shared_ptr<Plan> p = lookup_plan(plan);
+    return (p && p->slab) ? p : nullptr;
 }
 
 static int slab_direction(Plan *P, int direction, int *inverse) {
@@ -202,31 +208,36 @@ int fftb200_slab_plan_2d(fftb200_handle *plan, const int *n, fftb200_type type, 
 }
 
 int fftb200_slab_get_ipc_handle(fftb200_handle plan, void *handle64) {
-    Plan *P = lookup_slab(plan);
+    const std::shared_ptr<Plan> hold = lookup_slab(plan);
+    Plan *P = hold.get();
     if (!P || !handle64) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     return slab_get_ipc_handle(P, handle64);
 }
 
 int fftb200_slab_connect_ipc(fftb200_handle plan, const void *handles) {
-    Plan *P = lookup_slab(plan);
+    const std::shared_ptr<Plan> hold = lookup_slab(plan);
+    Plan *P = hold.get();
     if (!P || !handles) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     return slab_connect_ipc(P, handles);
 }
 
 int fftb200_slab_get_area(fftb200_handle plan, void **area, unsigned long long *bytes) {
-    Plan *P = lookup_slab(plan);
+    const std::shared_ptr<Plan> hold = lookup_slab(plan);
+    Plan *P = hold.get();
     if (!P || !area) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     return slab_get_area(P, area, bytes);
 }
 
 int fftb200_slab_connect_ptrs(fftb200_handle plan, void *const *areas) {
-    Plan *P = lookup_slab(plan);
+    const std::shared_ptr<Plan> hold = lookup_slab(plan);
+    Plan *P = hold.get();
     if (!P || !areas) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     return slab_connect_ptrs(P, areas);
 }
 
 int fftb200_slab_exec(fftb200_handle plan, const void *in, void *out, int direction) {
-    Plan *P = lookup_slab(plan);
+    const std::shared_ptr<Plan> hold = lookup_slab(plan);
+    Plan *P = hold.get();
     if (!P) return FFTB200_INVALID_PLAN;
     if (!in || !out) return FFTB200_INVALID_VALUE;
     int inverse = 0;
@@ -235,7 +246,8 @@ int fftb200_slab_exec(fftb200_handle plan, const void *in, void *out, int direct
 }
 
 int fftb200_slab_exec_pre(fftb200_handle plan, const void *in, void *send, int direction) {
-    Plan *P = lookup_slab(plan);
+    const std::shared_ptr<Plan> hold = lookup_slab(plan);
+    Plan *P = hold.get();
     if (!P) return FFTB200_INVALID_PLAN;
     if (!in || !send) return FFTB200_INVALID_VALUE;
     int inverse = 0;
@@ -245,7 +257,8 @@ int fftb200_slab_exec_pre(fftb200_handle plan, const void *in, void *send, int d
 }
 
 int fftb200_slab_exec_post(fftb200_handle plan, const void *recv, void *out, int direction) {
-    Plan *P = lookup_slab(plan);
+    const std::shared_ptr<Plan> hold = lookup_slab(plan);
+    Plan *P = hold.get();
     if (!P) return FFTB200_INVALID_PLAN;
     if (!recv || !out) return FFTB200_INVALID_VALUE;
     int inverse = 0;
@@ -255,13 +268,15 @@ int fftb200_slab_exec_post(fftb200_handle plan, const void *recv, void *out, int
 }
 
 int fftb200_slab_set_timing(fftb200_handle plan, int on) {
-    Plan *P = lookup_slab(plan);
+    const std::shared_ptr<Plan> hold = lookup_slab(plan);
+    Plan *P = hold.get();
     if (!P) return FFTB200_INVALID_PLAN;
     return slab_set_timing(P, on);
 }
 
 int fftb200_slab_get_phase_ms(fftb200_handle plan, float *ms) {
-    Plan *P = lookup_slab(plan);
+    const std::shared_ptr<Plan> hold = lookup_slab(plan);
+    Plan *P = hold.get();
     if (!P || !ms) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
     return slab_get_phase_ms(P, ms);
 }

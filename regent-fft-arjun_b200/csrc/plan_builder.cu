@@ -22,26 +22,29 @@
 namespace fftb200 {
 
 // ------------------------------------------------------------------------------------------
-// twiddles: w_n^m = exp(-2*pi*i*m/n), octant-reduced like fftw-3.3.8/kernel/trig.c:57-80, but
-// evaluated in long double before rounding (the accuracy contract of SURVEY.md §8 a10)
+// twiddles: w_n^m = exp(-2*pi*i*m/n), correctly rounded to within an ulp or so for every m (the accuracy
+// contract of SURVEY.md §8 a10: FFTW's tables come from an argument reduced to [0, pi/4] before libm sees it,
+// fftw-3.3.8/kernel/trig.c:57-80).  Here: the angle is m/n of a turn, an exact rational; count whole eighths of
+// a turn in integers (q = floor(8m/n), r = 8m - q*n), fold odd eighths back (r -> n - r) so the remaining angle
+// phi = (pi/4) * r/n lies in [0, pi/4], evaluate cos/sin of phi in long double, and place them by the table below.
 // ------------------------------------------------------------------------------------------
 static void twiddle(long long m, long long n, double *re, double *im) {
-    static const long double K2PI = 6.2831853071795864769252867665590057683943388L;
-    unsigned octant = 0;
-    long long quarter_n = n;
-    n *= 4;
-    m *= 4;
+    static const long double QUARTER_PI = 0.78539816339744830961566084581987572104929234984378L;
+    m %= n;
     if (m < 0) m += n;
-    if (m > n - m) { m = n - m; octant |= 4; }
-    if (m - quarter_n > 0) { m = m - quarter_n; octant |= 2; }
-    if (m > quarter_n - m) { m = quarter_n - m; octant |= 1; }
-    const long double theta = (K2PI * (long double)m) / (long double)n;
-    long double c = cosl(theta), s = sinl(theta), t;
-    if (octant & 1) { t = c; c = s; s = t; }
-    if (octant & 2) { t = c; c = -s; s = t; }
-    if (octant & 4) { s = -s; }
-    *re = (double)c;
-    *im = (double)(-s);  // forward sign
+    const long long q = (8 * m) / n;        // which eighth of the turn
+    long long r = 8 * m - q * n;            // position inside it, in units of 1/(8n) turn
+    if (q & 1) r = n - r;                   // odd eighths are measured back from their upper end
+    const long double phi = QUARTER_PI * (long double)r / (long double)n;
+    const long double c = cosl(phi), s = sinl(phi);
+    // (cos, sin) of the full angle for eighth q, from (c, s) of the folded angle
+    static const int cos_from_s[8] = {0, 1, 1, 0, 0, 1, 1, 0};
+    static const int cos_sign[8] = {+1, +1, -1, -1, -1, -1, +1, +1};
+    static const int sin_sign[8] = {+1, +1, +1, +1, -1, -1, -1, -1};
+    const long double co = cos_sign[q] * (cos_from_s[q] ? s : c);
+    const long double si = sin_sign[q] * (cos_from_s[q] ? c : s);
+    *re = (double)co;
+    *im = (double)(-si);  // forward transform: exp(-i theta)
 }
 
 int env_int_or(const char *name, int dflt) {
@@ -83,6 +86,33 @@ void *Builder::table(long long n, long long count, bool force_double, long long 
         d = upload(h.data(), h.size() * sizeof(float));
     }
     if (step == 1) cache[key] = d;
+    return d;
+}
+
+// first-stage twiddles of a ROW-load pass, transposed: t[(d-1)*(L/R) + u] = w_L^(d*u), d in [1,R), u in [0, L/R)
+void *Builder::table_stage1(long long L, int R) {
+    auto key = std::make_pair(std::make_pair(8, L), (long long)R);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    const long long TL = L / R, count = (long long)(R - 1) * TL;
+    void *d = nullptr;
+    if (P->prec == 1) {
+        std::vector<double> h(2 * (size_t)count);
+        for (long long dd = 1; dd < R; ++dd)
+            for (long long u = 0; u < TL; ++u) twiddle((dd * u) % L, L, &h[2 * ((dd - 1) * TL + u)], &h[2 * ((dd - 1) * TL + u) + 1]);
+        d = upload(h.data(), h.size() * sizeof(double));
+    } else {
+        std::vector<float> h(2 * (size_t)count);
+        for (long long dd = 1; dd < R; ++dd)
+            for (long long u = 0; u < TL; ++u) {
+                double re, im;
+                twiddle((dd * u) % L, L, &re, &im);
+                h[2 * ((dd - 1) * TL + u)] = (float)re;
+                h[2 * ((dd - 1) * TL + u) + 1] = (float)im;
+            }
+        d = upload(h.data(), h.size() * sizeof(float));
+    }
+    cache[key] = d;
     return d;
 }
 
@@ -140,8 +170,9 @@ bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long long ou
     ln.src = src;
     ln.dst = dst;
     TileParams &tp = ln.tp;
-    const int parts = ki->cluster * ki->split;  // CTAs that share one line
+    const int parts = ki->cluster;  // CTAs that share one line
     tp.tw = (L > ki->R) ? B.table(L / parts, L / parts, false) : nullptr;  // w_LL of the CTA-local stages
+    tp.tw_s1 = (load_row && L > ki->R) ? B.table_stage1(L, ki->R) : nullptr;
     tp.tw_aux = nullptr;
     if (parts > 1) tp.tw_aux = B.table(L, L, false);  // cross-CTA stage twiddles w_L
     if (variant == V_RR_R2C) tp.tw_aux = B.table(2ll * L, L / 2 + 1, false);
@@ -183,17 +214,6 @@ bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long long ou
         }
     }
     tp.ticket = nullptr;
-    {
-        // FFTB200_BULK=1: fetch column-pass tiles with the TMA engine; =2: only where the line stride exceeds 64 KiB
-        const int mode = env_int_or("FFTB200_BULK", 0);
-        const bool far = in_ls * (long long)(P->prec ? 16 : 8) > 65536;
-        if (mode > 0 && ki->fn_bulk && parts == 1 && lv[0].n % ki->W == 0 && (mode == 1 || far)) {
-            ln.bulk = true;
-            if (ki->smem_bytes > 48 * 1024)
-                cudaFuncSetAttribute((const void *)ki->fn_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, ki->smem_bytes);
-            cudaGetLastError();
-        }
-    }
     tp.prefetch_tiles = 0;
     {
         // L2 prefetch of the tile that will run next in this CTA slot (distance = CTAs resident on the GPU).
@@ -210,7 +230,7 @@ bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long long ou
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P->device);
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)ki->fn, ki->threads, ki->smem_bytes) != cudaSuccess)
                 cudaGetLastError();
-            tp.prefetch_tiles = k * sms * (per_sm > 0 ? per_sm : 1) / ki->split;
+            tp.prefetch_tiles = k * sms * (per_sm > 0 ? per_sm : 1);
         }
     }
     const long long lines = lv[0].n * lv[1].n * lv[2].n;
@@ -220,9 +240,9 @@ bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long long ou
     else
         ln.algo_bytes = (unsigned long long)lines * L * ce * 2ull;
     char buf[256];
-    snprintf(buf, sizeof buf, "tile %-11s %s L=%d R=%d W=%d threads=%d smem=%d cluster=%d split=%d lines=%lld tiles=%lld (%s)",
+    snprintf(buf, sizeof buf, "tile %-11s %s L=%d R=%d W=%d threads=%d smem=%d cluster=%d lines=%lld tiles=%lld (%s)",
              variant_name(variant), P->prec ? "fp64" : "fp32", L, ki->R, ki->W, ki->threads, ki->smem_bytes, ki->cluster,
-             ki->split, lines, tiles, what);
+             lines, tiles, what);
     ln.desc = buf;
     if (ki->smem_bytes > 48 * 1024) {
         if (cudaFuncSetAttribute((const void *)ki->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ki->smem_bytes) !=
@@ -252,77 +272,6 @@ static std::vector<int> split_1d(long long N, int prec) {
     }
     (void)prec;
     return f;
-}
-
-// Fuse the contiguous-axis pass and the following strided-axis pass into one persistent kernel when both
-// use the same CTA shape and the first pass's tiles enumerate whole planes in order (dense layouts).
-// FFTB200_NO_FUSE=1 keeps the separate passes (benchmarking only).
-static void try_fuse_first_two(Builder &B) {
-    Plan *P = B.P;
-    if (P->real || P->launches.size() < 2) return;
-    // Opt-in (FFTB200_FUSE=1).  Measured on B200 at 512^3 fp64: the fused kernel cuts HBM traffic of the two
-    // passes from 8.5 GB to 4.25 GB (ncu dram__bytes), but both forms are bound by per-tile latency at two
-    // CTAs per SM, not by HBM, and the ticket/flag traffic makes the fused form ~5 % slower (1.59 vs 1.51 ms).
-    const char *fu = getenv("FFTB200_FUSE");
-    if (!(fu && *fu && *fu != '0')) return;
-    Launch &a = P->launches[0], &b = P->launches[1];
-    if (a.kind != Launch::TILE || b.kind != Launch::TILE || a.variant != V_RR || b.variant != V_CC) return;
-    if (a.ki->cluster != 1 || b.ki->cluster != 1 || a.dst != BUF_OUT || b.src != BUF_OUT || b.dst != BUF_OUT) return;
-    const FusedKernelInfo *fk = find_fused_kernel(P->prec, a.ki->L, b.ki->L);
-    if (!fk) return;
-    if (a.ki->R != fk->RA || a.ki->W != fk->WA || b.ki->R != fk->RB || b.ki->W != fk->WB) return;
-    if (a.tp.n_tiles != a.tp.tiles_per_outer) return;  // pass A must be one dense run of rows
-    const long long planes = b.tp.n_tiles / b.tp.tiles_per_outer;
-    if (planes < 8 || a.tp.n_tiles % planes) return;
-    const long long ta_plane = a.tp.n_tiles / planes, tb_plane = b.tp.tiles_per_outer;
-    // rows of pass A per plane must equal the line length of pass B
-    if (ta_plane * a.ki->W != b.ki->L) return;
-    const long long want_tiles = env_int_or("FFTB200_FUSE_TILES", 128);  // benchmarking override
-    long long Pg = (want_tiles + ta_plane - 1) / ta_plane;
-    if (Pg < 1) Pg = 1;
-    while (Pg < planes && planes % Pg) ++Pg;
-    if (planes % Pg) return;
-    const long long n_groups = planes / Pg;
-    const int lag = env_int_or("FFTB200_FUSE_LAG", 2);
-    if (lag < 1 || n_groups < 2 * lag) return;
-    unsigned *counters = (unsigned *)B.alloc(sizeof(unsigned) * (size_t)(1 + n_groups));
-    if (!counters) return;
-    int sms = 148, per_sm = fk->min_ctas;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P->device);
-    if (fk->smem_bytes > 48 * 1024 &&
-        cudaFuncSetAttribute((const void *)fk->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fk->smem_bytes) != cudaSuccess) {
-        cudaGetLastError();
-        return;
-    }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fk->fn, fk->threads, fk->smem_bytes) != cudaSuccess ||
-        per_sm < 1) {
-        cudaGetLastError();
-        per_sm = 1;
-    }
-    Launch f = a;
-    f.kind = Launch::FUSED;
-    f.fk = fk;
-    f.tp_b = b.tp;
-    f.counters = counters;
-    f.tiles_a = (int)(ta_plane * Pg);
-    f.tiles_b = (int)(tb_plane * Pg);
-    f.n_groups = (int)n_groups;
-    f.lag = lag;
-    const long long total = (long long)(f.tiles_a + f.tiles_b) * n_groups;
-    f.grid = (unsigned)std::min<long long>(total, (long long)sms * per_sm);
-    f.src = a.src;
-    f.dst = BUF_OUT;
-    // compulsory HBM traffic of the fused pair: read the input once, write the result once
-    f.algo_bytes = a.algo_bytes;
-    char buf[320];
-    snprintf(buf, sizeof buf,
-             "fused row+col    %s L=%dx%d threads=%d smem=%d persistent grid=%u (%d CTAs/SM) groups=%d x %lld planes lag=%d "
-             "lines=%lld (last axis + next axis through L2)",
-             P->prec ? "fp64" : "fp32", a.ki->L, b.ki->L, fk->threads, fk->smem_bytes, f.grid, per_sm, f.n_groups, Pg, lag,
-             (long long)a.tp.n_tiles * a.ki->W);
-    f.desc = buf;
-    P->launches.erase(P->launches.begin(), P->launches.begin() + 2);
-    P->launches.insert(P->launches.begin(), f);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -434,9 +383,8 @@ static bool build_fast(Builder &B) {
         const size_t ce = P->prec ? 16 : 8;
         const bool dense = P->out_stride[3] == 1 && P->out_stride[2] == n[2] && P->out_stride[1] == n[1] * n[2];
         const bool far = (size_t)(n[1] * n[2]) * ce >= (256u << 10);
-        // (single-CTA tiles only: at 1024^3 the split kernel's middle pass loses more on the far stores, 8.1 -> 10.1 ms,
-        // than the last pass gains, 10.6 -> 9.3 ms)
-        const bool single = k1 && k0 && k1->cluster * k1->split == 1 && k0->cluster * k0->split == 1;
+        // (single-CTA tiles only.  1024^3 fp64, one 128 KiB tile per CTA: last pass 9.27 -> 7.09 ms, middle pass unchanged)
+        const bool single = k1 && k0 && k1->cluster == 1 && k0->cluster == 1;
         if (single && k1->W == k0->W && dense && far && n[2] % k1->W == 0) {
             const long long Wt = k1->W, nxb = n[2] / Wt;
             void *w = nullptr;
@@ -475,7 +423,6 @@ static bool build_fast(Builder &B) {
         first = false;
     }
     if (first) return false;
-    try_fuse_first_two(B);
     // in place is safe when every pass reads and writes the same addresses tile by tile
     bool same = !P->real;
     for (int d = 0; d <= rank; ++d) same = same && (P->in_stride[d] == P->out_stride[d]);

@@ -9,11 +9,7 @@
 namespace fftb200 {
 
 // one launch of a tile pass; cluster kernels go through cudaLaunchKernelEx with the cluster dimension
-cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st, const TileParams &tp, bool bulk) {
-    if (bulk && ki->fn_bulk) {
-        ki->fn_bulk<<<grid, ki->threads, ki->smem_bytes, st>>>(tp);
-        return cudaGetLastError();
-    }
+cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st, const TileParams &tp) {
     if (tp.ticket) {
         const cudaError_t e = cudaMemsetAsync(tp.ticket, 0, sizeof(unsigned), st);
         if (e != cudaSuccess) return e;
@@ -50,29 +46,35 @@ void free_plan_resources(Plan *p) {
     if (p->stage_in) cudaFree(p->stage_in);
     if (p->stage_out) cudaFree(p->stage_out);
     p->stage_in = p->stage_out = nullptr;
-    if (p->fallback) free_plan_resources(p->fallback.get());
+    p->fallback.reset();
 }
 
 // ------------------------------------------------------------------------------------------
 // handle table: handle = (generation << 32) | (slot + 1); never a raw pointer, so a stale or
 // zero-filled plan region (src/fft.rg:523-531) cannot crash the library
 // ------------------------------------------------------------------------------------------
+// Every ABI call holds a shared_ptr for its duration, so fftb200_destroy racing an exec / describe / timing
+// query on another thread (Legion runs destroy_plan from a CPU processor, src/fft.rg:624-645) cannot free the
+// plan under it: the resources go when the last holder returns (~Plan).
 static std::mutex g_mu;
-static std::vector<std::pair<unsigned, Plan *>> g_slots;  // (generation, plan)
+static std::vector<std::pair<unsigned, std::shared_ptr<Plan>>> g_slots;  // (generation, plan)
+
+Plan::~Plan() { free_plan_resources(this); }
 
 fftb200_handle register_plan(Plan *p) {
+    std::shared_ptr<Plan> sp(p);
     std::lock_guard<std::mutex> lk(g_mu);
     for (size_t i = 0; i < g_slots.size(); ++i)
         if (!g_slots[i].second) {
             g_slots[i].first++;
-            g_slots[i].second = p;
+            g_slots[i].second = std::move(sp);
             return ((fftb200_handle)g_slots[i].first << 32) | (fftb200_handle)(i + 1);
         }
-    g_slots.push_back({1u, p});
+    g_slots.push_back({1u, std::move(sp)});
     return ((fftb200_handle)1 << 32) | (fftb200_handle)g_slots.size();
 }
 
-Plan *lookup_plan(fftb200_handle h) {
+std::shared_ptr<Plan> lookup_plan(fftb200_handle h) {
     std::lock_guard<std::mutex> lk(g_mu);
     const size_t slot = (size_t)(h & 0xffffffffull);
     const unsigned gen = (unsigned)(h >> 32);
@@ -81,14 +83,14 @@ Plan *lookup_plan(fftb200_handle h) {
     return g_slots[slot - 1].second;
 }
 
-Plan *unregister_plan(fftb200_handle h) {
+std::shared_ptr<Plan> unregister_plan(fftb200_handle h) {
     std::lock_guard<std::mutex> lk(g_mu);
     const size_t slot = (size_t)(h & 0xffffffffull);
     const unsigned gen = (unsigned)(h >> 32);
     if (slot == 0 || slot > g_slots.size()) return nullptr;
     if (g_slots[slot - 1].first != gen) return nullptr;
-    Plan *p = g_slots[slot - 1].second;
-    g_slots[slot - 1].second = nullptr;
+    std::shared_ptr<Plan> p = std::move(g_slots[slot - 1].second);
+    g_slots[slot - 1].second.reset();
     return p;
 }
 
@@ -160,27 +162,7 @@ static int run_launches(Plan *P, const void *in, void *out, int inverse) {
             tp.out = dst;
             tp.inverse = inverse;
             tp.ticket = ln.ticket;
-            ce = launch_tile(ln.ki, ln.grid, P->stream, tp, ln.bulk);
-        } else if (ln.kind == Launch::FUSED) {
-            FusedParams fp;
-            fp.a = ln.tp;
-            fp.a.in = src;
-            fp.a.out = dst;
-            fp.a.inverse = inverse;
-            fp.b = ln.tp_b;
-            fp.b.in = dst;
-            fp.b.out = dst;
-            fp.b.inverse = inverse;
-            fp.counters = ln.counters;
-            fp.tiles_a = ln.tiles_a;
-            fp.tiles_b = ln.tiles_b;
-            fp.n_groups = ln.n_groups;
-            fp.lag = ln.lag;
-            ce = cudaMemsetAsync(ln.counters, 0, sizeof(unsigned) * (size_t)(1 + ln.n_groups), P->stream);
-            if (ce == cudaSuccess) {
-                ln.fk->fn<<<ln.grid, ln.fk->threads, ln.fk->smem_bytes, P->stream>>>(fp);
-                ce = cudaGetLastError();
-            }
+            ce = launch_tile(ln.ki, ln.grid, P->stream, tp);
         } else {
             ce = P->prec ? launch_generic<double>(ln, src, dst, inverse, P->stream)
                          : launch_generic<float>(ln, src, dst, inverse, P->stream);
@@ -239,18 +221,25 @@ int exec_plan(Plan *P, const void *in, void *out, int direction) {
 }
 
 static int exec_fallback(Plan *P, const void *in, void *out, int direction) {
+    Plan *fb = nullptr;
+    cudaStream_t st = nullptr;
     {
         std::lock_guard<std::mutex> lk(P->mu);
         if (!P->fallback) {
             DeviceGuard g(P->device);
-            Plan *fb = nullptr;
-            const int rc = create_plan(&fb, P->rank, P->n, P->batch, P->in_stride, P->out_stride, P->type, true);
+            Plan *made = nullptr;
+            const int rc = create_plan(&made, P->rank, P->n, P->batch, P->in_stride, P->out_stride, P->type, true);
             if (rc != FFTB200_SUCCESS) return rc;
-            P->fallback.reset(fb);
+            P->fallback.reset(made);
         }
-        P->fallback->stream = P->stream;
+        fb = P->fallback.get();
+        st = P->stream;
     }
-    return exec_plan(P->fallback.get(), in, out, direction);
+    {
+        std::lock_guard<std::mutex> lk(fb->mu);  // the fallback's stream is read under its own lock (exec_plan)
+        fb->stream = st;
+    }
+    return exec_plan(fb, in, out, direction);
 }
 
 }  // namespace fftb200

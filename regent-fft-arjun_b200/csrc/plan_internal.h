@@ -19,16 +19,11 @@ namespace fftb200 {
 enum BufSel { BUF_IN = 0, BUF_OUT = 1, BUF_WORK0 = 2, BUF_WORK1 = 3 };
 
 struct Launch {
-    enum Kind { TILE, FUSED, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER } kind = TILE;
+    enum Kind { TILE, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER } kind = TILE;
     // TILE
     const TileKernelInfo *ki = nullptr;
     TileParams tp{};
     int variant = 0;
-    // FUSED (two axis passes in one persistent kernel; tp = pass A, tp_b = pass B)
-    const FusedKernelInfo *fk = nullptr;
-    TileParams tp_b{};
-    unsigned *counters = nullptr;
-    int tiles_a = 0, tiles_b = 0, n_groups = 0, lag = 0;
     // generic
     GenLayout lay{};
     long long total = 0, outer = 0, inner = 0;
@@ -38,7 +33,6 @@ struct Launch {
     // common
     long long in_off = 0, out_off = 0;  // element offsets added to the source / destination base (chunked passes)
     unsigned *ticket = nullptr;         // persistent (capped) launches: dynamic tile counter, zeroed before every launch
-    bool bulk = false;                  // launch ki->fn_bulk (tile fetched by the TMA engine)
     int src = BUF_IN, dst = BUF_OUT;
     unsigned grid = 0;
     unsigned long long algo_bytes = 0;
@@ -76,6 +70,10 @@ struct Plan {
     long long in_stride[4] = {0, 0, 0, 0}, out_stride[4] = {0, 0, 0, 0};  // [batch, d0, d1, d2] elements
     std::unique_ptr<Plan> fallback;
     std::mutex mu;
+    Plan() = default;
+    Plan(const Plan &) = delete;
+    Plan &operator=(const Plan &) = delete;
+    ~Plan();  // releases every device resource (plan_exec.cu)
     size_t elt_in() const { return real ? (prec ? 8 : 4) : (prec ? 16 : 8); }
     size_t elt_out() const { return c2r ? (prec ? 8 : 4) : (prec ? 16 : 8); }
 };
@@ -94,13 +92,14 @@ struct DeviceGuard {
 
 // ---- plan_exec.cu ---------------------------------------------------------------------------------------
 // one launch of a tile pass; cluster kernels go through cudaLaunchKernelEx with the cluster dimension
-cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st, const TileParams &tp, bool bulk = false);
+cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st, const TileParams &tp);
 void free_plan_resources(Plan *p);
 int exec_plan(Plan *P, const void *in, void *out, int direction);
 // handle table: handle = (generation << 32) | (slot + 1); never a raw pointer
+// the table owns the plan; ABI calls hold a shared_ptr for their duration (destroy racing exec is safe)
 fftb200_handle register_plan(Plan *p);
-Plan *lookup_plan(fftb200_handle h);
-Plan *unregister_plan(fftb200_handle h);
+std::shared_ptr<Plan> lookup_plan(fftb200_handle h);
+std::shared_ptr<Plan> unregister_plan(fftb200_handle h);
 
 // ---- plan_builder.cu ------------------------------------------------------------------------------------
 int env_int_or(const char *name, int dflt);  // tuning knobs, read at plan creation
@@ -117,6 +116,7 @@ struct Builder {
     void *upload(const void *host, size_t bytes);
     // w_n^(k*step) for k in [0, count), in the plan's precision or always fp64 (force_double)
     void *table(long long n, long long count, bool force_double, long long step = 1);
+    void *table_stage1(long long L, int R);  // transposed first-stage twiddles of a ROW-load pass
     void *alloc(size_t bytes);
 };
 

@@ -15,8 +15,11 @@ static table_fn k_tables[2][V_COUNT] = {
 const TileKernelInfo *find_tile_kernel(int prec, int variant, int L) {
     int n = 0;
     const TileKernelInfo *t = k_tables[prec][variant](&n);
-    // FFTB200_TILE_ALT=k (tuning experiments only): take the k-th alternative row compiled for this length
-    const char *alt = getenv("FFTB200_TILE_ALT");
+    // FFTB200_TILE_ALT=k (tuning experiments only): take the k-th alternative row compiled for this length;
+    // FFTB200_TILE_ALT_ROW / FFTB200_TILE_ALT_COL do the same for contiguous-axis / strided-axis passes only
+    const bool row_only = (variant == V_RR || variant == V_RR_R2C || variant == V_RR_C2R);
+    const char *alt = getenv(row_only ? "FFTB200_TILE_ALT_ROW" : "FFTB200_TILE_ALT_COL");
+    if (!(alt && *alt)) alt = getenv("FFTB200_TILE_ALT");
     int skip = (alt && *alt) ? atoi(alt) : 0;
     const TileKernelInfo *first = nullptr;
     for (int i = 0; i < n; ++i)

@@ -45,6 +45,7 @@ struct SlabState {
     bool peer_mapped[MAX_PEERS] = {};
     bool connected = false;
     unsigned long long epoch = 0;
+    int *err_host = nullptr;  // mapped host word: a wait kernel that gave up sets it; every later exec reports it
     cudaStream_t aux = nullptr;
     std::vector<cudaEvent_t> ev_chunk;
     cudaEvent_t ev_done = nullptr, ev_t[5] = {};
@@ -83,15 +84,41 @@ __global__ void slab_signal_kernel(SlabPeers peers, int G, int me, int kind, uns
     if (d < G) st_release_sys(peers.flags[d] + (size_t)kind * MAX_PEERS + me, epoch);
 }
 
+// A rank whose exec failed half-way (or that never called exec) must not leave its peers' GPUs spinning for ever:
+// the wait gives up after SLAB_WAIT_TIMEOUT_NS and records the failure in the plan's mapped error word, which every
+// later exec on that plan reports as FFTB200_EXEC_FAILED.  (Single-process use: a host thread must not issue calls
+// that synchronise all devices - cudaMalloc/cudaFree with peer mappings - between its own exec and its peers'.)
+constexpr unsigned long long SLAB_WAIT_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // one thread per source rank: wait until its slot (kind, src) in MY flags reached `epoch`
-__global__ void slab_wait_kernel(const unsigned long long *flags, int G, int kind, unsigned long long epoch) {
+__global__ void slab_wait_kernel(const unsigned long long *flags, int G, int kind, unsigned long long epoch, int *err) {
     const int s = threadIdx.x;
     if (s < G) {
         const unsigned long long *f = flags + (size_t)kind * MAX_PEERS + s;
-        while (ld_acquire_sys(f) < epoch) __nanosleep(200);
+        const unsigned long long t0 = global_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys(f) < epoch) {
+            __nanosleep(200);
+            if ((++spins & 0x3ff) == 0 && global_ns() - t0 > SLAB_WAIT_TIMEOUT_NS) {
+                *reinterpret_cast<volatile int *>(err) = 1 + kind;
+                break;
+            }
+        }
     }
     __syncthreads();
     __threadfence_system();
+}
+
+// all kinds at once: lets every peer's pending and future waits of this epoch terminate (failure path)
+__global__ void slab_release_all_kernel(SlabPeers peers, int G, int me, unsigned long long epoch) {
+    const int d = threadIdx.x & (MAX_PEERS - 1), kind = threadIdx.x / MAX_PEERS;
+    if (d < G && kind < 64) st_release_sys(peers.flags[d] + (size_t)kind * MAX_PEERS + me, epoch);
 }
 
 void slab_free(Plan *P) {
@@ -101,6 +128,7 @@ void slab_free(Plan *P) {
         if (S->peer_mapped[d] && S->peer_area[d]) cudaIpcCloseMemHandle(S->peer_area[d]);
     if (S->tmp) cudaFree(S->tmp);
     if (S->area) cudaFree(S->area);
+    if (S->err_host) cudaFreeHost(S->err_host);
     if (S->aux) cudaStreamDestroy(S->aux);
     for (cudaEvent_t e : S->ev_chunk) cudaEventDestroy(e);
     if (S->ev_done) cudaEventDestroy(S->ev_done);
@@ -163,11 +191,11 @@ int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, in
         return code;
     };
     // chunking of the contiguous index (multiples of 16 columns keep every segment >= 128 B).
-    // chunks <= 0: automatic — 4 for single-CTA tiles (measured best on 2 x B200 at 512^3), 1 when the
-    // y-axis pass is a split or cluster kernel (1024^3 R2C on 4 x B200: 4.77 ms unchunked, 6.32 ms with 4 chunks)
+    // chunks <= 0: automatic — 4 for single-CTA tiles of at most 64 KiB (measured best on 2 x B200 at 512^3), 1 when
+    // the y-axis pass is a cluster kernel or owns the SM (128 KiB tiles: the overlapped pass could not co-reside)
     if (chunks <= 0) {
         const TileKernelInfo *k2 = find_tile_kernel(P->prec, V_CC_PEER, n[1]);
-        chunks = (G > 1 && k2 && k2->cluster == 1 && k2->split == 1) ? 4 : 1;
+        chunks = (G > 1 && k2 && k2->cluster == 1 && k2->smem_bytes <= 64 * 1024) ? 4 : 1;
     }
     long long cw = (S->n2c + chunks - 1) / chunks;
     cw = (cw + 15) / 16 * 16;
@@ -181,6 +209,8 @@ int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, in
     S->area_bytes = S->flags_off + sizeof(unsigned long long) * MAX_PEERS * 64;
     if (cudaMalloc(&S->area, S->area_bytes) != cudaSuccess) { cudaGetLastError(); return fail(FFTB200_ALLOC_FAILED); }
     if (cudaMemset((char *)S->area + S->flags_off, 0, S->area_bytes - S->flags_off) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
+    if (cudaHostAlloc((void **)&S->err_host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return fail(FFTB200_ALLOC_FAILED); }
+    *S->err_host = 0;
     P->work_bytes = (size_t)vol * ce;
 
     // ---- pass 1: x axis, in [n0l][n1][n2] -> tmp [n0l][n1][n2c]
@@ -348,6 +378,8 @@ int slab_create_2d(Plan **out, const int *n, fftb200_type type, int rank, int G)
     S->area_bytes = S->flags_off + sizeof(unsigned long long) * MAX_PEERS * 64;
     if (cudaMalloc(&S->area, S->area_bytes) != cudaSuccess) { cudaGetLastError(); return fail(FFTB200_ALLOC_FAILED); }
     if (cudaMemset((char *)S->area + S->flags_off, 0, S->area_bytes - S->flags_off) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
+    if (cudaHostAlloc((void **)&S->err_host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return fail(FFTB200_ALLOC_FAILED); }
+    *S->err_host = 0;
     P->work_bytes = S->recv_bytes;
     {   // pass A: rows of n1 (contiguous) -> column k of the transpose lives on rank k / n1l
         std::vector<Level> lv = {{S->n0l, S->n1, 1}};
@@ -378,30 +410,22 @@ static unsigned long long *slab_flags(SlabState *S, int d) {
 }
 
 // fused exchange: every rank calls this once per transform (collective)
-int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
+static int slab_exec_p2p_body(Plan *P, const void *in, void *out, int inverse, const SlabPeers &peers, void *const *recv,
+                              unsigned long long epoch) {
     SlabState *S = P->slab;
-    if (!S->connected) return FFTB200_INVALID_PLAN;
-    DeviceGuard g(P->device);
-    std::lock_guard<std::mutex> lk(P->mu);
     cudaStream_t st = P->stream;
-    const unsigned long long epoch = ++S->epoch;
-    SlabPeers peers;
-    void *recv[MAX_PEERS];
-    for (int d = 0; d < MAX_PEERS; ++d) {
-        peers.flags[d] = d < S->G ? slab_flags(S, d) : nullptr;
-        recv[d] = d < S->G ? S->peer_area[d] : nullptr;
-    }
+    const unsigned long long *myflags = slab_flags(S, S->rank);
     if (S->timing) cudaEventRecord(S->ev_t[0], st);
     // my receive buffer is free again (stream order: after my previous transform's pass 3)
     if (S->G > 1) slab_signal_kernel<<<1, 32, 0, st>>>(peers, S->G, S->rank, 0, epoch);
     if (S->two_d) {
-        if (S->G > 1) slab_wait_kernel<<<1, 32, 0, st>>>(slab_flags(S, S->rank), S->G, 0, epoch);
+        if (S->G > 1) slab_wait_kernel<<<1, 32, 0, st>>>(myflags, S->G, 0, epoch, S->err_host);
         if (S->timing) cudaEventRecord(S->ev_t[1], st);
         int rc2 = slab_launch(P, S->l_2a, in, nullptr, recv, inverse, st);
         if (rc2) return rc2;
         if (S->G > 1) {
             slab_signal_kernel<<<1, 32, 0, st>>>(peers, S->G, S->rank, 1, epoch);
-            slab_wait_kernel<<<1, 32, 0, st>>>(slab_flags(S, S->rank), S->G, 1, epoch);
+            slab_wait_kernel<<<1, 32, 0, st>>>(myflags, S->G, 1, epoch, S->err_host);
         }
         if (S->timing) cudaEventRecord(S->ev_t[2], st);
         rc2 = slab_launch(P, S->l_2b, S->area, out, nullptr, inverse, st);
@@ -411,7 +435,7 @@ int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
     }
     if (!P->real) {
         // y axis + exchange (plane chunks) -> x axis on arrived chunks (second stream) -> z axis
-        if (S->G > 1) slab_wait_kernel<<<1, 32, 0, st>>>(slab_flags(S, S->rank), S->G, 0, epoch);
+        if (S->G > 1) slab_wait_kernel<<<1, 32, 0, st>>>(myflags, S->G, 0, epoch, S->err_host);
         if (S->timing) cudaEventRecord(S->ev_t[1], st);
         for (int c = 0; c < S->Jp; ++c) {
             int rc2 = slab_launch(P, S->l_y[c], in, nullptr, recv, inverse, st);
@@ -423,7 +447,7 @@ int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
                 cudaEventRecord(S->ev_chunk[c], st);
                 cudaStreamWaitEvent(sx, S->ev_chunk[c], 0);
             }
-            if (S->G > 1) slab_wait_kernel<<<1, 32, 0, sx>>>(slab_flags(S, S->rank), S->G, 1 + c, epoch);
+            if (S->G > 1) slab_wait_kernel<<<1, 32, 0, sx>>>(myflags, S->G, 1 + c, epoch, S->err_host);
             rc2 = slab_launch(P, S->l_x[c], S->area, S->area, nullptr, inverse, sx);
             if (rc2) return rc2;
         }
@@ -439,7 +463,7 @@ int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
     int rc = slab_launch(P, S->l_pass1, in, S->tmp, nullptr, inverse, st);
     if (rc) return rc;
     if (S->timing) cudaEventRecord(S->ev_t[1], st);
-    if (S->G > 1) slab_wait_kernel<<<1, 32, 0, st>>>(slab_flags(S, S->rank), S->G, 0, epoch);
+    if (S->G > 1) slab_wait_kernel<<<1, 32, 0, st>>>(myflags, S->G, 0, epoch, S->err_host);
     for (int j = 0; j < S->J; ++j) {
         rc = slab_launch(P, S->l_pass2[j], S->tmp, nullptr, recv, inverse, st);
         if (rc) return rc;
@@ -450,7 +474,7 @@ int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
             cudaEventRecord(S->ev_chunk[j], st);
             cudaStreamWaitEvent(s3, S->ev_chunk[j], 0);
         }
-        if (S->G > 1) slab_wait_kernel<<<1, 32, 0, s3>>>(slab_flags(S, S->rank), S->G, 1 + j, epoch);
+        if (S->G > 1) slab_wait_kernel<<<1, 32, 0, s3>>>(myflags, S->G, 1 + j, epoch, S->err_host);
         rc = slab_launch(P, S->l_pass3[j], S->area, out, nullptr, inverse, s3);
         if (rc) return rc;
     }
@@ -460,6 +484,32 @@ int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
     }
     if (S->timing) cudaEventRecord(S->ev_t[3], st);
     return cudaGetLastError() == cudaSuccess ? FFTB200_SUCCESS : FFTB200_EXEC_FAILED;
+}
+
+int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
+    SlabState *S = P->slab;
+    if (!S->connected) return FFTB200_INVALID_PLAN;
+    if (*reinterpret_cast<volatile int *>(S->err_host) != 0) return FFTB200_EXEC_FAILED;  // an earlier hand-shake timed out
+    DeviceGuard g(P->device);
+    std::lock_guard<std::mutex> lk(P->mu);
+    const unsigned long long epoch = ++S->epoch;
+    SlabPeers peers;
+    void *recv[MAX_PEERS];
+    for (int d = 0; d < MAX_PEERS; ++d) {
+        peers.flags[d] = d < S->G ? slab_flags(S, d) : nullptr;
+        recv[d] = d < S->G ? S->peer_area[d] : nullptr;
+    }
+    const int rc = slab_exec_p2p_body(P, in, out, inverse, peers, recv, epoch);
+    if (rc != FFTB200_SUCCESS && S->G > 1) {
+        // a launch failed in the middle of the collective: publish every flag of this epoch anyway so that the peers'
+        // wait kernels terminate (their result is garbage, they learn of it through the caller's error handling),
+        // and poison this plan
+        cudaGetLastError();
+        slab_release_all_kernel<<<1, 1024, 0, P->stream>>>(peers, S->G, S->rank, epoch);
+        cudaGetLastError();
+        *S->err_host = 100;
+    }
+    return rc;
 }
 
 int slab_exec_pre(Plan *P, const void *in, void *send, int inverse) {

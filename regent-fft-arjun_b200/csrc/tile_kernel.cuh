@@ -53,7 +53,8 @@ struct TileParams {
     const void *in;
     void *out;
     const void *tw;      // w_L^k, k in [0,L), forward sign, complex<T>
-    const void *tw_aux;  // V_RR_R2C: w_{2L}^k, k in [0, L/2]; V_RR_C2R: k in [0, L); cluster/split: w_L^k; complex<T>
+    const void *tw_s1;   // ROW-load variants: first-stage twiddles transposed, tw_s1[(d-1)*(L/R) + u] = w_L^(d*u), complex<T>
+    const void *tw_aux;  // V_RR_R2C: w_{2L}^k, k in [0, L/2]; V_RR_C2R: k in [0, L); cluster: w_L^k; complex<T>
     const double2 *tw4_hi;  // V_CC_TW: w_N^(m) = hi[m >> tw4_shift] * lo[m & tw4_mask]
     const double2 *tw4_lo;
     long long in_ls, in_is, in_os1, in_os2;
@@ -98,9 +99,11 @@ template <typename T, int L_, int R_, int W_, int VAR_> struct TileTraits {
     // data fits 32 registers per thread: caps the kernel at 64 registers
     static constexpr int MIN_CTAS_BY_THREADS = 1024 / THREADS < 1 ? 1 : (1024 / THREADS > 8 ? 8 : 1024 / THREADS);
     static constexpr int MIN_CTAS_BY_SMEM = SMEM_BYTES == 0 ? 8 : (200 * 1024 / SMEM_BYTES < 1 ? 1 : 200 * 1024 / SMEM_BYTES);
-    static constexpr int MIN_CTAS = (int)sizeof(cplx<T>) * R > 128
-                                        ? 1
-                                        : (MIN_CTAS_BY_THREADS < MIN_CTAS_BY_SMEM ? MIN_CTAS_BY_THREADS : MIN_CTAS_BY_SMEM);
+    // ... and at 128 registers (as many CTAs as then fit the 64 K register file) when the payload is 64 registers
+    static constexpr int MIN_CTAS_BY_REGS128 = 512 / THREADS < 1 ? 1 : 512 / THREADS;
+    static constexpr int MIN_CTAS_SMALL = MIN_CTAS_BY_THREADS < MIN_CTAS_BY_SMEM ? MIN_CTAS_BY_THREADS : MIN_CTAS_BY_SMEM;
+    static constexpr int MIN_CTAS_BIG = MIN_CTAS_BY_REGS128 < MIN_CTAS_BY_SMEM ? MIN_CTAS_BY_REGS128 : MIN_CTAS_BY_SMEM;
+    static constexpr int MIN_CTAS = (int)sizeof(cplx<T>) * R > 128 ? MIN_CTAS_BIG : MIN_CTAS_SMALL;
     static_assert(R * T_LINE == L, "R must divide L");
     static_assert(S == 1 || R_LAST <= R, "bad stage split");
 };
@@ -118,38 +121,11 @@ template <int BITS, int TOTAL_BITS> __device__ __forceinline__ int swz_fold(int 
 }
 
 template <typename T> __device__ __forceinline__ cplx<T> ld_cplx(const cplx<T> *p) { return __ldg(p); }
-// Tile data is touched exactly once per pass: load it evict-first / store it streaming so that it does not
-// push the twiddle tables (re-read by every CTA) out of L1.
-// (measured on B200: streaming hints make the 512^3 passes 5-10 % slower, so they stay off)
-#ifndef FFTB200_STREAMING
-#define FFTB200_STREAMING 0
-#endif
-__device__ __forceinline__ double2 ld_noalloc(const double2 *p) {
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float2 ld_noalloc(const float2 *p) {
-    float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    return v;
-}
-template <typename T> __device__ __forceinline__ cplx<T> ld_data(const cplx<T> *p) {
-#if FFTB200_STREAMING == 1
-    return __ldcs(p);
-#elif FFTB200_STREAMING == 2
-    return ld_noalloc(p);  // keep L1 for the twiddle tables
-#else
-    return __ldg(p);
-#endif
-}
-template <typename T> __device__ __forceinline__ void st_data(cplx<T> *p, cplx<T> v) {
-#if FFTB200_STREAMING
-    __stcs(p, v);
-#else
-    *p = v;
-#endif
-}
+// Tile data is touched exactly once per pass.  Streaming cache hints (ld.global.cs / st.global.cs) and
+// ld.global.nc.L1::no_allocate were measured on B200 and made the 512^3 passes 5-10 % slower / no different,
+// so tile data uses the default policies (DESIGN.md "Experiments").
+template <typename T> __device__ __forceinline__ cplx<T> ld_data(const cplx<T> *p) { return __ldg(p); }
+template <typename T> __device__ __forceinline__ void st_data(cplx<T> *p, cplx<T> v) { *p = v; }
 
 // ---------------------------------------------------------------------------------------------
 // All radix stages of one tile.  In: thread (w1, u1) holds x[u1 + d*T_LINE], d < R, of line w1 in v[].
@@ -157,8 +133,9 @@ template <typename T> __device__ __forceinline__ void st_data(cplx<T> *p, cplx<T
 // (w1,u1) follows the load style, (wl,ul) the store style.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int L, int R, int W, int VAR>
-__device__ __forceinline__ void tile_stages(cplx<T> *v, cplx<T> *sm, const cplx<T> *__restrict__ tw, const int w1,
-                                            const int u1, const int w_col, const int u_col, const int wl, const int ul) {
+__device__ __forceinline__ void tile_stages(cplx<T> *v, cplx<T> *sm, const cplx<T> *__restrict__ tw,
+                                            const cplx<T> *__restrict__ tw_s1, const int w1, const int u1, const int w_col,
+                                            const int u_col, const int wl, const int ul) {
     using TR = TileTraits<T, L, R, W, VAR>;
     constexpr int S = TR::S;
     constexpr int LOG_R = TR::LOG_R, LOG_W = TR::LOG_W, LOG_L = TR::LOG_L;
@@ -168,10 +145,17 @@ __device__ __forceinline__ void tile_stages(cplx<T> *v, cplx<T> *sm, const cplx<
     constexpr int SB = TR::SWZ_BITS;
     if constexpr (S > 1) {
         fft_reg<T, R>(v);
-        // twiddle w_L^(d*u1), then park at position d*m_1 + u1
+        // twiddle w_L^(d*u1), then park at position d*m_1 + u1.  ROW loads: the lanes of a warp run along u1, so
+        // tw[d*u1] would be a gather with a lane stride of d elements (up to 32 different 128-byte lines per warp
+        // load: 15 such loads per thread cost several times the tile's own data loads in L1 cycles); the transposed
+        // per-stage table makes every one of them one contiguous 512-byte run.  COL loads: the lanes run along the
+        // tile's lines first and share their twiddles, so the plain table is already cheap.
         {
 #pragma unroll
-            for (int d = 1; d < R; ++d) v[d] = cmul(v[d], ld_cplx<T>(tw + d * u1));
+            for (int d = 1; d < R; ++d) {
+                if constexpr (TR::LOAD_ROW) v[d] = cmul(v[d], ld_cplx<T>(tw_s1 + (d - 1) * T_LINE + u1));
+                else v[d] = cmul(v[d], ld_cplx<T>(tw + d * u1));
+            }
             const int base = (u1 << LOG_W) | w1;
             const int fb = swz_fold<SB, IDX_BITS>(base);
 #pragma unroll
@@ -324,13 +308,8 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
     }
 }
 
-// DATA_CG: read the tile with ld.global.cg (L2-coherent).  Needed when the data was written earlier in the
-// SAME kernel by other SMs (fused two-axis pass): the read-only / L1 path could return stale lines.
-// BULK: the tile is fetched by the TMA engine (cp.async.bulk, one 128-byte row segment per request, completion
-// counted by an mbarrier) straight into shared memory instead of through registers; column passes only.
-template <typename T, int L, int R, int W, int VAR, bool DATA_CG = false, bool BULK = false>
-__device__ __forceinline__ void fft_tile_body(const TileParams &p, const int tile, unsigned char *smem_raw,
-                                              const unsigned mbar = 0) {
+template <typename T, int L, int R, int W, int VAR>
+__device__ __forceinline__ void fft_tile_body(const TileParams &p, const int tile, unsigned char *smem_raw) {
     using TR = TileTraits<T, L, R, W, VAR>;
     using C = cplx<T>;
     constexpr int S = TR::S;
@@ -359,43 +338,13 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
     // ------------------------------------------------------------------ stage 1: HBM -> registers
     const int w1 = TR::LOAD_ROW ? w_row : w_col;
     const int u1 = TR::LOAD_ROW ? u_row : u_col;
-    if constexpr (BULK) {
-        static_assert(!TR::LOAD_ROW && !TR::SWIZZLED, "bulk loads fill the unswizzled column-pass layout");
-        constexpr unsigned ROW_BYTES = (unsigned)(W * sizeof(C));
-        const unsigned sm_addr = (unsigned)__cvta_generic_to_shared(sm);
-        if (t == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)L * ROW_BYTES) : "memory");
-        const C *src0 = gin + (long long)i0 * p.in_is;  // whole tiles only (the plan guarantees it)
-        for (int r = t; r < L; r += TR::THREADS) {
-            const C *row = src0 + (long long)r * p.in_ls;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             sm_addr + (unsigned)r * ROW_BYTES),
-                         "l"(row), "r"(ROW_BYTES), "r"(mbar)
-                         : "memory");
-        }
-        unsigned done = 0;
-        while (!done) {
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done)
-                         : "r"(mbar), "r"(0u)
-                         : "memory");
-        }
-#pragma unroll
-        for (int d = 0; d < R; ++d) {
-            C x = sm[((u1 + d * T_LINE) << LOG_W) | w1];
-            if (inv) { T s = x.x; x.x = x.y; x.y = s; }
-            v[d] = x;
-        }
-    } else {
+    {
         const bool ok = (i0 + w1) < p.n_inner;
         const C *src = gin + (long long)(i0 + w1) * p.in_is + (long long)u1 * p.in_ls;
 #pragma unroll
         for (int d = 0; d < R; ++d) {
             C x = mk<T>((T)0, (T)0);
-            if (ok) {
-                if constexpr (DATA_CG) x = __ldcg(src + (long long)(d * T_LINE) * p.in_ls);
-                else x = ld_data<T>(src + (long long)(d * T_LINE) * p.in_ls);
-            }
+            if (ok) x = ld_data<T>(src + (long long)(d * T_LINE) * p.in_ls);
             if (inv && VAR != V_RR_C2R) { T s = x.x; x.x = x.y; x.y = s; }
             v[d] = x;
         }
@@ -469,7 +418,7 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
 
     const int wl = TR::STORE_ROW ? w_row : w_col;
     const int ul = TR::STORE_ROW ? u_row : u_col;
-    tile_stages<T, L, R, W, VAR>(v, sm, tw, w1, u1, w_col, u_col, wl, ul);
+    tile_stages<T, L, R, W, VAR>(v, sm, tw, reinterpret_cast<const C *>(p.tw_s1), w1, u1, w_col, u_col, wl, ul);
 
     // After the last stage thread (wl, ul) holds, for b in [0,B) and q in [0,R_LAST):
     //   X[k],  k = (ul + b*T_LINE) + q*(L/R_LAST),  in v[b*R_LAST + q]
@@ -554,198 +503,6 @@ fft_tile_kernel(const TileParams p) {
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         fft_tile_body<T, L, R, W, VAR>(p, tile, smem_raw);
         if (TileTraits<T, L, R, W, VAR>::NEED_SMEM && tile + (int)gridDim.x < p.n_tiles) __syncthreads();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Fused two-axis pass: the contiguous-axis pass (A, ROW/ROW) and the next strided-axis pass (B, COL/COL,
-// in place on A's output) of a multi-dimensional transform in ONE persistent kernel, ordered so that B
-// reads A's output while it is still in the 126 MB L2: the intermediate never has to come back from HBM.
-//
-// Work is cut into groups of whole planes.  CTAs draw tickets from a global counter; the ticket order is
-//   A(0) A(1) .. A(lag-1) | A(lag) B(0) | A(lag+1) B(1) | ... | B(n_groups-1)
-// A(g)/B(g) = the tiles of group g.  A tile of B(g) waits (acquire-spin on done[g]) until all tiles of
-// A(g) have been stored; those tiles were handed out at least `lag` slots earlier, i.e. to CTAs that are
-// running or finished, so the wait cannot deadlock and is normally already satisfied.
-// ---------------------------------------------------------------------------------------------
-struct FusedParams {
-    TileParams a, b;
-    unsigned *counters;  // [0] ticket dispenser, [1 + g] finished A tiles of group g (zeroed before the launch)
-    int tiles_a, tiles_b;  // per group
-    int n_groups, lag;
-};
-
-template <typename T, int LA, int RA, int WA, int LB, int RB, int WB>
-__global__ void __launch_bounds__(TileTraits<T, LA, RA, WA, V_RR>::THREADS, TileTraits<T, LA, RA, WA, V_RR>::MIN_CTAS)
-fft_fused_ab_kernel(const FusedParams p) {
-    using TA = TileTraits<T, LA, RA, WA, V_RR>;
-    using TB = TileTraits<T, LB, RB, WB, V_CC>;
-    static_assert(TA::THREADS == TB::THREADS, "both passes must use the same CTA shape");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_ticket[2];
-    const int per_slot = p.tiles_a + p.tiles_b;
-    const int head = p.lag * p.tiles_a;                          // tickets of the A-only slots
-    const int mid = (p.n_groups - p.lag) * per_slot;             // slots with both
-    const int total = p.n_groups * per_slot;
-    int cur = 0;
-    if (threadIdx.x == 0) s_ticket[0] = (int)atomicAdd(p.counters, 1u);
-    __syncthreads();
-    for (;;) {
-        const int ticket = s_ticket[cur];
-        if (ticket >= total) break;
-        // draw the next ticket now; its L2 round trip hides behind this tile (consumed at the loop end)
-        unsigned next_ticket = 0;
-        if (threadIdx.x == 0) next_ticket = atomicAdd(p.counters, 1u);
-        bool is_b;
-        int g, t;
-        if (ticket < head) {
-            is_b = false; g = ticket / p.tiles_a; t = ticket - g * p.tiles_a;
-        } else if (ticket < head + mid) {
-            const int r = ticket - head;
-            const int slot = r / per_slot, q = r - slot * per_slot;
-            if (q < p.tiles_a) { is_b = false; g = p.lag + slot; t = q; }
-            else { is_b = true; g = slot; t = q - p.tiles_a; }
-        } else {
-            const int r = ticket - head - mid;
-            is_b = true; g = (p.n_groups - p.lag) + r / p.tiles_b; t = r % p.tiles_b;
-        }
-        if (!is_b) {
-            fft_tile_body<T, LA, RA, WA, V_RR, false>(p.a, g * p.tiles_a + t, smem_raw);
-            __syncthreads();  // all stores of the tile issued
-            // the last warp publishes the tile; warp 0 is free to go on with the next ticket
-            if (threadIdx.x == TA::THREADS - 1) {
-                __threadfence();
-                atomicAdd(p.counters + 1 + g, 1u);
-            }
-        } else {
-            if (threadIdx.x == 0) {
-                const unsigned *f = p.counters + 1 + g;
-                unsigned v;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                    if (v < (unsigned)p.tiles_a) __nanosleep(100);
-                } while (v < (unsigned)p.tiles_a);
-            }
-            __syncthreads();
-            fft_tile_body<T, LB, RB, WB, V_CC, true>(p.b, g * p.tiles_b + t, smem_raw);
-        }
-        if (threadIdx.x == 0) s_ticket[cur ^ 1] = (int)next_ticket;
-        __syncthreads();  // next ticket visible; shared memory of this tile free
-        cur ^= 1;
-    }
-}
-
-// Column pass whose tile is fetched by the TMA engine (see BULK above); one tile per CTA.
-template <typename T, int L, int R, int W, int VAR>
-__global__ void __launch_bounds__(TileTraits<T, L, R, W, VAR>::THREADS, TileTraits<T, L, R, W, VAR>::MIN_CTAS)
-fft_tile_bulk_kernel(const TileParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long mbar_storage;
-    const unsigned mbar = (unsigned)__cvta_generic_to_shared(&mbar_storage);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    fft_tile_body<T, L, R, W, VAR, false, true>(p, (int)blockIdx.x, smem_raw, mbar);
-}
-
-template <typename T, int L, int R, int W, int VAR> constexpr void (*bulk_kernel_or_null())(const TileParams) {
-    if constexpr (VAR == V_CC && !TileTraits<T, L, R, W, VAR>::SWIZZLED && TileTraits<T, L, R, W, VAR>::S > 1)
-        return &fft_tile_bulk_kernel<T, L, R, W, VAR>;
-    else
-        return nullptr;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Split pass for strided axes of L = 2*LL points without a cluster: the two CTAs of a tile each read the
-// WHOLE tile (both halves of every line: 2x the L2->SM traffic, but the second reader hits L2, so HBM traffic
-// stays 1x), form their half of the first radix-2 stage on the fly,
-//     y_c[j] = (x[j] + (-1)^c x[j+LL]) * w_L^(j*c),      c = CTA parity, j < LL,
-// and then run the ordinary length-LL pipeline and store rows c + 2k'.  No DSMEM, no cluster barrier: the two
-// CTAs are independent, which matters because these passes are bound by per-tile latency (measured on B200 at
-// 1024^3: cluster-of-2 kernel 11.3 ms per pass).
-// ---------------------------------------------------------------------------------------------
-template <typename T, int LL, int CL, int R, int W, int VAR>
-__global__ void __launch_bounds__(TileTraits<T, LL, R, W, VAR>::THREADS, TileTraits<T, LL, R, W, VAR>::MIN_CTAS)
-fft_split_kernel(const TileParams p) {
-    using TR = TileTraits<T, LL, R, W, VAR>;
-    using C = cplx<T>;
-    static_assert(CL == 2, "split passes halve the line");
-    static_assert(!TR::LOAD_ROW && !TR::STORE_ROW && TR::S > 1, "split passes are column passes");
-    constexpr int LOG_W = TR::LOG_W;
-    constexpr int T_LINE = TR::T_LINE;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C *sm = reinterpret_cast<C *>(smem_raw);
-    const int t = threadIdx.x;
-    const int w = t & (W - 1), u = t >> LOG_W;
-    const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);       // w_LL^k
-    const C *__restrict__ twL = reinterpret_cast<const C *>(p.tw_aux);  // w_L^k
-    const bool inv = p.inverse != 0;
-    const int work = p.n_tiles * CL;
-    __shared__ int s_wi[2];
-    int cur = 0;
-    const bool dynamic = p.ticket != nullptr;
-    if (dynamic) {
-        if (t == 0) s_wi[0] = (int)atomicAdd(p.ticket, 1u);
-        __syncthreads();
-    }
-    for (int wi = dynamic ? s_wi[0] : (int)blockIdx.x; wi < work;) {
-        unsigned next = 0;
-        if (dynamic && t == 0) next = atomicAdd(p.ticket, 1u);
-        const int tile = wi / CL, c = wi - tile * CL;
-        const int o = tile / p.tiles_per_outer;
-        const int i0 = (tile - o * p.tiles_per_outer) * W;
-        const int o1 = o / p.n_o2, o2 = o - o1 * p.n_o2;
-        const C *__restrict__ gin = reinterpret_cast<const C *>(p.in) + o1 * p.in_os1 + o2 * p.in_os2;
-        // L2 prefetch of the tile this CTA slot runs next (issued by the c == 0 CTA for both halves)
-        if (p.prefetch_tiles > 0 && c == 0) {
-            const int ft = tile + p.prefetch_tiles;
-            if (ft < p.n_tiles) {
-                const int fo = ft / p.tiles_per_outer;
-                const int fi0 = (ft - fo * p.tiles_per_outer) * W;
-                const int fo1 = fo / p.n_o2, fo2 = fo - fo1 * p.n_o2;
-                if (fi0 + W <= p.n_inner) {
-                    const C *fin = reinterpret_cast<const C *>(p.in) + fo1 * p.in_os1 + fo2 * p.in_os2 + (long long)fi0 * p.in_is;
-                    constexpr int CH_ROW = (W * (int)sizeof(C) + 127) / 128;
-                    for (int ch = t; ch < CL * LL * CH_ROW; ch += TR::THREADS) {
-                        const int r = ch / CH_ROW, cc = ch - r * CH_ROW;
-                        const char *a = reinterpret_cast<const char *>(fin + (long long)r * p.in_ls) + cc * 128;
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-                    }
-                }
-            }
-        }
-        C v[R];
-        {
-            const bool ok = (i0 + w) < p.n_inner;
-            const C *src = gin + (long long)(i0 + w) * p.in_is + (long long)u * p.in_ls;
-#pragma unroll
-            for (int d = 0; d < R; ++d) {
-                C a = mk<T>((T)0, (T)0), b = mk<T>((T)0, (T)0);
-                if (ok) {
-                    a = ld_data<T>(src + (long long)(d * T_LINE) * p.in_ls);
-                    b = ld_data<T>(src + (long long)(LL + d * T_LINE) * p.in_ls);
-                }
-                if (inv) { T s = a.x; a.x = a.y; a.y = s; s = b.x; b.x = b.y; b.y = s; }
-                if (c == 0) {
-                    v[d] = cadd(a, b);
-                } else {
-                    v[d] = cmul(csub(a, b), ld_cplx<T>(twL + (u + d * T_LINE)));
-                }
-            }
-        }
-        tile_stages<T, LL, R, W, VAR>(v, sm, tw, w, u, w, u, w, u);
-        tile_store<T, LL, R, W, VAR>(v, p, o1, o2, i0, w, u, CL, c);
-        if (dynamic) {
-            if (t == 0) s_wi[cur ^ 1] = (int)next;
-            __syncthreads();
-            cur ^= 1;
-            wi = s_wi[cur];
-        } else {
-            wi += (int)gridDim.x;
-            if (wi < work) __syncthreads();
-        }
     }
 }
 
@@ -857,7 +614,7 @@ fft_cluster_kernel(const TileParams p) {
             const int idx = ((u + d * T_LINE) << LOG_W) | w;
             v[d] = sm[idx ^ swz_fold<SB, IDX_BITS>(idx)];
         }
-        tile_stages<T, LL, R, W, VAR>(v, sm, tw, w, u, w, u, w, u);
+        tile_stages<T, LL, R, W, VAR>(v, sm, tw, nullptr, w, u, w, u, w, u);
         tile_store<T, LL, R, W, VAR>(v, p, o1, o2, i0, w, u, CL, c);
         // persistent launch: nobody may scatter the next tile into a CTA that still works on this one
         if (tile + n_clusters < p.n_tiles) cluster.sync();

@@ -8,17 +8,7 @@ struct TileKernelInfo {
     void (*fn)(const TileParams);
     int L, R, W, threads, smem_bytes;
     int cluster;  // CTAs per thread-block cluster (1 = ordinary launch); L = cluster * (length one CTA holds)
-    int split;    // independent CTAs per tile (fft_split_kernel; 1 otherwise); L = split * (length one CTA holds)
-    void (*fn_bulk)(const TileParams);  // same pass with the tile fetched by the TMA engine (column passes), or nullptr
 };
-
-struct FusedKernelInfo {
-    void (*fn)(const FusedParams);
-    int LA, LB, threads, smem_bytes, min_ctas;
-    int RA, WA, RB, WB;  // the tile shapes the kernel was compiled for: the plan's passes must match them
-};
-// fused contiguous-axis + strided-axis pass for lengths (LA, LB); nullptr when not compiled
-const FusedKernelInfo *find_fused_kernel(int prec, int LA, int LB);
 
 // prec: 0 = fp32 (complex32), 1 = fp64 (complex64).  Returns nullptr when L is not compiled.
 const TileKernelInfo *find_tile_kernel(int prec, int variant, int L);

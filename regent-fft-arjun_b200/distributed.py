@@ -189,19 +189,52 @@ class SlabFFT3D:
                              "hbm_GB/s": self.local_pass_bytes / t / 1e9, "nvlink_GB/s_out": self.exchange_bytes_out / t / 1e9,
                              "ideal_ms_overlapped": max(hbm_t, nvl_t) * 1e3, "ideal_ms_serial": (hbm_t + nvl_t) * 1e3}}
 
-    def make_host_step(self, x_dev: torch.Tensor):
-        """e2e step: this rank's slab starts in pinned host memory and the result ends there."""
-        hx = torch.empty(self.local_in_shape, dtype=self.dtype_in.torch, pin_memory=True)
-        hy = torch.empty(self.local_out_shape, dtype=self.dtype_out.torch, pin_memory=True)
-        hx.copy_(x_dev)
-        xin = torch.empty_like(x_dev)
+    def make_host_pipeline(self, x_dev: torch.Tensor, slots: int = 2):
+        """e2e steps: this rank's slab starts in pinned host memory and the result ends there.
 
-        def step():
-            xin.copy_(hx, non_blocking=True)
-            self.execute(xin)
-            hy.copy_(self.out, non_blocking=True)
+        `slots` transforms are in flight: slot s owns a pinned input, a device input, a device output and a pinned
+        output; host->device copies, the slab transform (collective, on the current stream) and device->host copies
+        run on three streams chained by events, so step k's D2H and step k+1's H2D overlap step k's/k+1's
+        transform on the full-duplex host link.  Returns (run(nsteps), h2d_bytes, d2h_bytes, host_outputs).
+        run() records its end on the current stream (the caller times with events there).
+        """
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        hx = [torch.empty(self.local_in_shape, dtype=self.dtype_in.torch, pin_memory=True) for _ in range(slots)]
+        hy = [torch.empty(self.local_out_shape, dtype=self.dtype_out.torch, pin_memory=True) for _ in range(slots)]
+        xin = [torch.empty_like(x_dev) for _ in range(slots)]
+        outs = [torch.empty_like(self.out) for _ in range(slots)]
+        for h in hx:
+            h.copy_(x_dev)
+        ev_in = [torch.cuda.Event() for _ in range(slots)]      # H2D of the slot finished
+        ev_fft = [torch.cuda.Event() for _ in range(slots)]     # transform of the slot finished (xin free, out ready)
+        ev_out = [torch.cuda.Event() for _ in range(slots)]     # D2H of the slot finished (out free)
+        torch.cuda.synchronize(dev)
 
-        return step, hx.numel() * hx.element_size(), hy.numel() * hy.element_size()
+        def run(nsteps: int):
+            s_in.wait_stream(cur)
+            s_out.wait_stream(cur)
+            for k in range(nsteps):
+                s = k % slots
+                with torch.cuda.stream(s_in):
+                    if k >= slots:
+                        s_in.wait_event(ev_fft[s])          # the previous transform of this slot has read xin[s]
+                    xin[s].copy_(hx[s], non_blocking=True)
+                    ev_in[s].record(s_in)
+                cur.wait_event(ev_in[s])
+                if k >= slots:
+                    cur.wait_event(ev_out[s])               # the previous result of this slot has left outs[s]
+                self.execute(xin[s], outs[s])
+                ev_fft[s].record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_fft[s])
+                    hy[s].copy_(outs[s], non_blocking=True)
+                    ev_out[s].record(s_out)
+            cur.wait_stream(s_out)
+            cur.wait_stream(s_in)
+
+        return run, hx[0].numel() * hx[0].element_size(), hy[0].numel() * hy[0].element_size(), hy
 
     def gather_natural(self, out: torch.Tensor | None = None) -> np.ndarray:
         """all ranks: the full result in natural order [n0][n1][n2c] (tests; not a hot path)"""
