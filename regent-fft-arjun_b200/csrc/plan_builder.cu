@@ -89,28 +89,30 @@ void *Builder::table(long long n, long long count, bool force_double, long long 
     return d;
 }
 
-// first-stage twiddles of a ROW-load pass, transposed: t[(d-1)*(L/R) + u] = w_L^(d*u), d in [1,R), u in [0, L/R)
-void *Builder::table_stage1(long long L, int R) {
+// per-stage transposed twiddle tables of a tile pipeline of length L and radix R (layout: tile_kernel.cuh,
+// TileParams::tw / stage_tw_offset)
+void *Builder::stage_tables(long long L, int R) {
     auto key = std::make_pair(std::make_pair(8, L), (long long)R);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
-    const long long TL = L / R, count = (long long)(R - 1) * TL;
+    std::vector<double> h;
+    long long scale = 1;  // R^(s-1)
+    for (long long m = L / R; m >= 1 && scale * R < L; m /= R, scale *= R) {
+        for (long long d = 1; d < R; ++d)
+            for (long long lo = 0; lo < m; ++lo) {
+                double re, im;
+                twiddle((d * lo * scale) % L, L, &re, &im);
+                h.push_back(re);
+                h.push_back(im);
+            }
+    }
+    if (h.empty()) { h.push_back(1.0); h.push_back(0.0); }
     void *d = nullptr;
     if (P->prec == 1) {
-        std::vector<double> h(2 * (size_t)count);
-        for (long long dd = 1; dd < R; ++dd)
-            for (long long u = 0; u < TL; ++u) twiddle((dd * u) % L, L, &h[2 * ((dd - 1) * TL + u)], &h[2 * ((dd - 1) * TL + u) + 1]);
         d = upload(h.data(), h.size() * sizeof(double));
     } else {
-        std::vector<float> h(2 * (size_t)count);
-        for (long long dd = 1; dd < R; ++dd)
-            for (long long u = 0; u < TL; ++u) {
-                double re, im;
-                twiddle((dd * u) % L, L, &re, &im);
-                h[2 * ((dd - 1) * TL + u)] = (float)re;
-                h[2 * ((dd - 1) * TL + u) + 1] = (float)im;
-            }
-        d = upload(h.data(), h.size() * sizeof(float));
+        std::vector<float> hf(h.begin(), h.end());
+        d = upload(hf.data(), hf.size() * sizeof(float));
     }
     cache[key] = d;
     return d;
@@ -171,8 +173,7 @@ bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long long ou
     ln.dst = dst;
     TileParams &tp = ln.tp;
     const int parts = ki->cluster;  // CTAs that share one line
-    tp.tw = (L > ki->R) ? B.table(L / parts, L / parts, false) : nullptr;  // w_LL of the CTA-local stages
-    tp.tw_s1 = (load_row && L > ki->R) ? B.table_stage1(L, ki->R) : nullptr;
+    tp.tw = (L / parts > ki->R) ? B.stage_tables(L / parts, ki->R) : nullptr;  // stage twiddles of the CTA-local length
     tp.tw_aux = nullptr;
     if (parts > 1) tp.tw_aux = B.table(L, L, false);  // cross-CTA stage twiddles w_L
     if (variant == V_RR_R2C) tp.tw_aux = B.table(2ll * L, L / 2 + 1, false);

@@ -116,7 +116,7 @@ struct Builder {
     void *upload(const void *host, size_t bytes);
     // w_n^(k*step) for k in [0, count), in the plan's precision or always fp64 (force_double)
     void *table(long long n, long long count, bool force_double, long long step = 1);
-    void *table_stage1(long long L, int R);  // transposed first-stage twiddles of a ROW-load pass
+    void *stage_tables(long long L, int R);  // per-stage transposed twiddle tables of one tile pipeline
     void *alloc(size_t bytes);
 };
 

@@ -52,8 +52,9 @@ constexpr int MAX_PEERS = 16;
 struct TileParams {
     const void *in;
     void *out;
-    const void *tw;      // w_L^k, k in [0,L), forward sign, complex<T>
-    const void *tw_s1;   // ROW-load variants: first-stage twiddles transposed, tw_s1[(d-1)*(L/R) + u] = w_L^(d*u), complex<T>
+    const void *tw;      // per-stage twiddle tables of the CTA-local length, transposed so that a warp reads them as
+                         // contiguous runs: stage s < S at offset stage_tw_offset(s), entry [(d-1)*m_s + lo] =
+                         // w_L^(d * lo * R^(s-1)), d in [1,R), lo in [0, m_s), m_s = L / R^s; forward sign, complex<T>
     const void *tw_aux;  // V_RR_R2C: w_{2L}^k, k in [0, L/2]; V_RR_C2R: k in [0, L); cluster: w_L^k; complex<T>
     const double2 *tw4_hi;  // V_CC_TW: w_N^(m) = hi[m >> tw4_shift] * lo[m & tw4_mask]
     const double2 *tw4_lo;
@@ -75,6 +76,12 @@ struct TileParams {
 };
 
 constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
+// offset (in complex elements) of stage s's table inside TileParams::tw; stage_tw_offset(L, R, S) = total size
+__host__ __device__ constexpr int stage_tw_offset(int L, int R, int s) {
+    int off = 0, m = L / R;
+    for (int q = 1; q < s; ++q) { off += (R - 1) * m; m /= R; }
+    return off;
+}
 
 template <typename T, int L_, int R_, int W_, int VAR_> struct TileTraits {
     static constexpr int L = L_, R = R_, W = W_, VAR = VAR_;
@@ -133,9 +140,8 @@ template <typename T> __device__ __forceinline__ void st_data(cplx<T> *p, cplx<T
 // (w1,u1) follows the load style, (wl,ul) the store style.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int L, int R, int W, int VAR>
-__device__ __forceinline__ void tile_stages(cplx<T> *v, cplx<T> *sm, const cplx<T> *__restrict__ tw,
-                                            const cplx<T> *__restrict__ tw_s1, const int w1, const int u1, const int w_col,
-                                            const int u_col, const int wl, const int ul) {
+__device__ __forceinline__ void tile_stages(cplx<T> *v, cplx<T> *sm, const cplx<T> *__restrict__ tw, const int w1,
+                                            const int u1, const int w_col, const int u_col, const int wl, const int ul) {
     using TR = TileTraits<T, L, R, W, VAR>;
     constexpr int S = TR::S;
     constexpr int LOG_R = TR::LOG_R, LOG_W = TR::LOG_W, LOG_L = TR::LOG_L;
@@ -145,17 +151,13 @@ __device__ __forceinline__ void tile_stages(cplx<T> *v, cplx<T> *sm, const cplx<
     constexpr int SB = TR::SWZ_BITS;
     if constexpr (S > 1) {
         fft_reg<T, R>(v);
-        // twiddle w_L^(d*u1), then park at position d*m_1 + u1.  ROW loads: the lanes of a warp run along u1, so
-        // tw[d*u1] would be a gather with a lane stride of d elements (up to 32 different 128-byte lines per warp
-        // load: 15 such loads per thread cost several times the tile's own data loads in L1 cycles); the transposed
-        // per-stage table makes every one of them one contiguous 512-byte run.  COL loads: the lanes run along the
-        // tile's lines first and share their twiddles, so the plain table is already cheap.
+        // twiddle w_L^(d*u1), then park at position d*m_1 + u1.  The tables are stored per stage and transposed
+        // ([d][lo]): with a plain w_L^k table the lanes of a warp (which run along u1 on ROW loads) would gather with a
+        // stride of d elements - up to 32 different 128-byte lines per warp load, 15 such loads per thread, several
+        // times the tile's own data loads in L1 cycles; transposed, every load is one contiguous run.
         {
 #pragma unroll
-            for (int d = 1; d < R; ++d) {
-                if constexpr (TR::LOAD_ROW) v[d] = cmul(v[d], ld_cplx<T>(tw_s1 + (d - 1) * T_LINE + u1));
-                else v[d] = cmul(v[d], ld_cplx<T>(tw + d * u1));
-            }
+            for (int d = 1; d < R; ++d) v[d] = cmul(v[d], ld_cplx<T>(tw + (d - 1) * T_LINE + u1));
             const int base = (u1 << LOG_W) | w1;
             const int fb = swz_fold<SB, IDX_BITS>(base);
 #pragma unroll
@@ -184,10 +186,10 @@ __device__ __forceinline__ void tile_stages(cplx<T> *v, cplx<T> *sm, const cplx<
                 v[d] = sm[(base | dbits) ^ fb ^ swz_fold<SB, IDX_BITS>(dbits)];
             }
             fft_reg<T, R>(v);
-            // twiddle w_{m_{s-1}}^(d*lo) = w_L^(d*lo*R^(s-1))
-            const int tstep = lo << (LOG_R * (s - 1));
+            // twiddle w_{m_{s-1}}^(d*lo) = w_L^(d*lo*R^(s-1)): stage table [d][lo]
+            const cplx<T> *tws = tw + stage_tw_offset(L, R, s) + lo;
 #pragma unroll
-            for (int d = 1; d < R; ++d) v[d] = cmul(v[d], ld_cplx<T>(tw + d * tstep));
+            for (int d = 1; d < R; ++d) v[d] = cmul(v[d], ld_cplx<T>(tws + ((d - 1) << log_ms)));
 #pragma unroll
             for (int d = 0; d < R; ++d) {
                 const int dbits = (d << log_ms) << LOG_W;
@@ -418,7 +420,7 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
 
     const int wl = TR::STORE_ROW ? w_row : w_col;
     const int ul = TR::STORE_ROW ? u_row : u_col;
-    tile_stages<T, L, R, W, VAR>(v, sm, tw, reinterpret_cast<const C *>(p.tw_s1), w1, u1, w_col, u_col, wl, ul);
+    tile_stages<T, L, R, W, VAR>(v, sm, tw, w1, u1, w_col, u_col, wl, ul);
 
     // After the last stage thread (wl, ul) holds, for b in [0,B) and q in [0,R_LAST):
     //   X[k],  k = (ul + b*T_LINE) + q*(L/R_LAST),  in v[b*R_LAST + q]
@@ -614,7 +616,7 @@ fft_cluster_kernel(const TileParams p) {
             const int idx = ((u + d * T_LINE) << LOG_W) | w;
             v[d] = sm[idx ^ swz_fold<SB, IDX_BITS>(idx)];
         }
-        tile_stages<T, LL, R, W, VAR>(v, sm, tw, nullptr, w, u, w, u, w, u);
+        tile_stages<T, LL, R, W, VAR>(v, sm, tw, w, u, w, u, w, u);
         tile_store<T, LL, R, W, VAR>(v, p, o1, o2, i0, w, u, CL, c);
         // persistent launch: nobody may scatter the next tile into a CTA that still works on this one
         if (tile + n_clusters < p.n_tiles) cluster.sync();

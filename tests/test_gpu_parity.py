@@ -221,8 +221,8 @@ def test_shapes_against_oracle(L, oracle, kind):
 
 
 def test_long_strided_axes_use_cluster_kernels(L, oracle, monkeypatch):
-    """strided axes of 1024 points run as one 128 KiB tile per CTA, 2048..16384 as thread-block-cluster
-    passes (DSMEM cross stage); the cluster-of-2 kernel for 1024 stays selectable"""
+    """strided axes of 1024 and 2048 points run as one 128 KiB tile per CTA, 4096..16384 as thread-block-cluster
+    passes (DSMEM cross stage); the cluster kernels for 1024 and 2048 stay selectable"""
     for kind, shape in [("z2z", (1024, 64)), ("z2z", (2048, 8)), ("z2z", (4096, 16)), ("z2z", (8192, 8)),
                         ("c2c", (1024, 32)), ("c2c", (2048, 16)), ("c2c", (4096, 48 // 3)), ("c2c", (8192, 16)),
                         ("c2c", (16384, 8)), ("d2z", (4096, 64)), ("r2c", (2048, 128))]:
@@ -231,18 +231,18 @@ def test_long_strided_axes_use_cluster_kernels(L, oracle, monkeypatch):
         got, desc = gpu_fft(L, kind, x, shape)
         err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape))
         assert err <= oracle.tolerance(int(np.prod(shape)), kind in ("c2c", "r2c")), (kind, shape, err)
-        want = {1024: "smem=131072 cluster=1", 2048: "cluster=4", 4096: "cluster=8", 8192: "cluster=8", 16384: "cluster=8"}[shape[0]]
+        want = {1024: "smem=131072 cluster=1", 2048: "smem=131072 cluster=1", 4096: "cluster=8", 8192: "cluster=8", 16384: "cluster=8"}[shape[0]]
         assert want in desc, desc
         # backward transform through the same kernels
         if kind in ("z2z", "c2c"):
             back, _ = gpu_fft(L, kind, got, shape, direction=+1)
             assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * oracle.tolerance(int(np.prod(shape)), kind == "c2c")
     monkeypatch.setenv("FFTB200_TILE_ALT_COL", "1")      # the cluster-of-2 alternative for L = 1024
-    for kind, shape in [("z2z", (1024, 64)), ("c2c", (1024, 32))]:
+    for kind, shape in [("z2z", (1024, 64)), ("c2c", (1024, 32)), ("z2z", (2048, 16)), ("c2c", (2048, 32))]:
         _, dt_in, _ = _kinds(L)[kind]
         x = oracle.synth(shape, dt_in, 650)
         got, desc = gpu_fft(L, kind, x, shape)
-        assert "cluster=2" in desc, desc
+        assert ("cluster=2" if shape[0] == 1024 else "cluster=4") in desc, desc
         assert oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape)) <= oracle.tolerance(int(np.prod(shape)), kind == "c2c")
 
 
