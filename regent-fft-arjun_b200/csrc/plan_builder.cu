@@ -200,6 +200,8 @@ bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long long ou
     tp.in_os1 = lv[2].is;
     tp.out_os1 = lv[2].os;
     tp.tiles_per_outer = (int)((lv[0].n + ki->W - 1) / ki->W);
+    fast_div_make(tp.tiles_per_outer, &tp.div_tpo_m, &tp.div_tpo_s);
+    fast_div_make(tp.n_o2, &tp.div_o2_m, &tp.div_o2_s);
     tp.inverse = 0;
     const long long tiles = (long long)tp.tiles_per_outer * lv[1].n * lv[2].n;
     if (tiles <= 0 || tiles > 0x7fffffffll) return false;

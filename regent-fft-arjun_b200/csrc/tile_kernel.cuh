@@ -67,8 +67,11 @@ struct TileParams {
     int n_inner;   // lines along the inner index
     int n_o2;      // outer index o = o1*n_o2 + o2
     int tiles_per_outer;
+    // divisions by tiles_per_outer / n_o2 as multiply-high + shift (fast_div below): every thread of every tile splits
+    // its tile index (and the prefetched tile's) into (o1, o2, i0)
+    unsigned div_tpo_m, div_tpo_s, div_o2_m, div_o2_s;
     int tw4_shift, tw4_mask;
-    int inverse;   // swap re/im on load and store (backward transform)
+    int inverse;   // backward transform: conjugate on load and on store
     // V_CC_PEER: output line index k goes to buffer peer[k >> peer_shift] at line (k & peer_mask);
     // the o1/o2/i offsets and out_ls apply inside that buffer
     void *peer[MAX_PEERS];
@@ -76,6 +79,18 @@ struct TileParams {
 };
 
 constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
+// x / d for 0 <= x < 2^31 and a divisor known at plan time: d == 1 -> m = 0; else l = ceil(log2 d), m = ceil(2^(31+l) / d)
+// (fits 32 bits), s = l - 1 and x / d == umulhi(x, m) >> s exactly (Granlund & Montgomery, N = 31)
+__host__ __device__ inline void fast_div_make(int d, unsigned *m, unsigned *s) {
+    if (d <= 1) { *m = 0; *s = 0; return; }
+    int l = 0;
+    while ((1ll << l) < d) ++l;
+    *m = (unsigned)(((1ull << (31 + l)) + (unsigned long long)d - 1) / (unsigned long long)d);
+    *s = (unsigned)(l - 1);
+}
+__device__ __forceinline__ int fast_div(int x, unsigned m, unsigned s) {
+    return m ? (int)(__umulhi((unsigned)x, m) >> s) : x;
+}
 // offset (in complex elements) of stage s's table inside TileParams::tw; stage_tw_offset(L, R, S) = total size
 __host__ __device__ constexpr int stage_tw_offset(int L, int R, int s) {
     int off = 0, m = L / R;
@@ -128,6 +143,16 @@ template <int BITS, int TOTAL_BITS> __device__ __forceinline__ int swz_fold(int 
 }
 
 template <typename T> __device__ __forceinline__ cplx<T> ld_cplx(const cplx<T> *p) { return __ldg(p); }
+// Backward transforms run through the forward butterflies as conj(F(conj(x))): the imaginary part's sign bit is
+// flipped on load and on store (one integer XOR each; `mask` is 0 for forward transforms, the sign bit otherwise).
+__device__ __forceinline__ double2 conj_if(double2 x, unsigned mask) {
+    x.y = __hiloint2double(__double2hiint(x.y) ^ (int)mask, __double2loint(x.y));
+    return x;
+}
+__device__ __forceinline__ float2 conj_if(float2 x, unsigned mask) {
+    x.y = __int_as_float(__float_as_int(x.y) ^ (int)mask);
+    return x;
+}
 // Tile data is touched exactly once per pass.  Streaming cache hints (ld.global.cs / st.global.cs) and
 // ld.global.nc.L1::no_allocate were measured on B200 and made the 512^3 passes 5-10 % slower / no different,
 // so tile data uses the default policies (DESIGN.md "Experiments").
@@ -240,7 +265,7 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
     constexpr int T_LINE = TR::T_LINE;
     constexpr int B = (S > 1) ? R / TR::R_LAST : 1;
     constexpr int RL = (S > 1) ? TR::R_LAST : R;
-    const bool inv = p.inverse != 0;
+    const unsigned cmask = p.inverse ? 0x80000000u : 0u;
     const bool ok = (i0 + wl) < p.n_inner;
     const long long off = o1 * p.out_os1 + o2 * p.out_os2 + (long long)(i0 + wl) * p.out_is;
     C *dst = reinterpret_cast<C *>(p.out) + off;
@@ -273,39 +298,54 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
         sb.y = sq.y = 0.0;
         if (B > 1 && RECUR_B) sb = lookup(i * (long long)(kmul * T_LINE));
         if (RL > 1) sq = lookup(i * (long long)(kmul * (L / RL)));
+        // output addresses advance by fixed strides over b and q: two 64-bit adds per store, no multiplies
+        const long long step_q = (long long)(kmul * (L / RL)) * p.out_ls, step_b = (long long)(kmul * T_LINE) * p.out_ls;
+        C *pb = dst + (long long)(kadd + kmul * ul) * p.out_ls;
 #pragma unroll
         for (int b = 0; b < B; ++b) {
             double2 wq = wb;
+            C *pq = pb;
 #pragma unroll
             for (int q = 0; q < RL; ++q) {
-                const int k = kadd + kmul * ((ul + b * T_LINE) + q * (L / RL));
                 C x = v[b * RL + q];
                 const double xr = (double)x.x * wq.x - (double)x.y * wq.y;
                 const double xi = (double)x.x * wq.y + (double)x.y * wq.x;
                 x.x = (T)xr; x.y = (T)xi;
-                if (inv) { T s2 = x.x; x.x = x.y; x.y = s2; }
-                if (ok) st_data<T>(dst + (long long)k * p.out_ls, x);
+                x = conj_if(x, cmask);
+                if (ok) st_data<T>(pq, x);
+                pq += step_q;
                 if (q + 1 < RL) wq = mul(wq, sq);
             }
+            pb += step_b;
             if (b + 1 < B) {
                 if constexpr (RECUR_B) wb = mul(wb, sb);
                 else wb = lookup(i * (long long)(kadd + kmul * (ul + (b + 1) * T_LINE)));
             }
         }
-    } else {
+    } else if constexpr (VAR == V_CC_PEER || VAR == V_RC_PEER) {
 #pragma unroll
-    for (int b = 0; b < B; ++b)
+        for (int b = 0; b < B; ++b)
 #pragma unroll
-        for (int q = 0; q < RL; ++q) {
-            const int k = kadd + kmul * ((ul + b * T_LINE) + q * (L / RL));
-            C x = v[b * RL + q];
-            if (inv) { T s = x.x; x.x = x.y; x.y = s; }
-            if constexpr (VAR == V_CC_PEER || VAR == V_RC_PEER) {
+            for (int q = 0; q < RL; ++q) {
+                const int k = kadd + kmul * ((ul + b * T_LINE) + q * (L / RL));
+                const C x = conj_if(v[b * RL + q], cmask);
                 C *pd = reinterpret_cast<C *>(p.peer[k >> p.peer_shift]) + off;
                 if (ok) pd[(long long)(k & p.peer_mask) * p.out_ls] = x;
-            } else {
-                if (ok) st_data<T>(dst + (long long)k * p.out_ls, x);
             }
+    } else {
+        // output index k = kadd + kmul * ((ul + b*T_LINE) + q*(L/RL)): the address advances by fixed strides over b and
+        // q, two 64-bit adds per store instead of a 64-bit multiply each (the store phase was ~19 instructions per STG)
+        const long long step_q = (long long)(kmul * (L / RL)) * p.out_ls, step_b = (long long)(kmul * T_LINE) * p.out_ls;
+        C *pb = dst + (long long)(kadd + kmul * ul) * p.out_ls;
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            C *pq = pb;
+#pragma unroll
+            for (int q = 0; q < RL; ++q) {
+                if (ok) st_data<T>(pq, conj_if(v[b * RL + q], cmask));
+                pq += step_q;
+            }
+            pb += step_b;
         }
     }
 }
@@ -327,13 +367,13 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
     const int w_col = t & (W - 1), u_col = t >> LOG_W;
     const int u_row = t & (T_LINE - 1), w_row = t >> LOG_TL;
 
-    const int o = tile / p.tiles_per_outer;
+    const int o = fast_div(tile, p.div_tpo_m, p.div_tpo_s);
     const int i0 = (tile - o * p.tiles_per_outer) * W;
-    const int o1 = o / p.n_o2, o2 = o - o1 * p.n_o2;
+    const int o1 = fast_div(o, p.div_o2_m, p.div_o2_s), o2 = o - o1 * p.n_o2;
     const C *__restrict__ gin = reinterpret_cast<const C *>(p.in) + o1 * p.in_os1 + o2 * p.in_os2;
     C *__restrict__ gout = reinterpret_cast<C *>(p.out) + o1 * p.out_os1 + o2 * p.out_os2;
     const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);
-    const bool inv = p.inverse != 0;
+    const unsigned cmask = (p.inverse && VAR != V_RR_C2R) ? 0x80000000u : 0u;
 
     C v[R];
 
@@ -341,14 +381,15 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
     const int w1 = TR::LOAD_ROW ? w_row : w_col;
     const int u1 = TR::LOAD_ROW ? u_row : u_col;
     {
-        const bool ok = (i0 + w1) < p.n_inner;
-        const C *src = gin + (long long)(i0 + w1) * p.in_is + (long long)u1 * p.in_ls;
+        // lines past the end of a ragged last tile re-read the last valid line (their results are never stored):
+        // no predicates or zero fills on the load path
+        const int wi = min(i0 + w1, p.n_inner - 1);
+        const C *src = gin + (long long)wi * p.in_is + (long long)u1 * p.in_ls;
+        const long long step = (long long)T_LINE * p.in_ls;
 #pragma unroll
         for (int d = 0; d < R; ++d) {
-            C x = mk<T>((T)0, (T)0);
-            if (ok) x = ld_data<T>(src + (long long)(d * T_LINE) * p.in_ls);
-            if (inv && VAR != V_RR_C2R) { T s = x.x; x.x = x.y; x.y = s; }
-            v[d] = x;
+            v[d] = conj_if(ld_data<T>(src), cmask);
+            src += step;
         }
     }
 
@@ -356,9 +397,9 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
     if (p.prefetch_tiles > 0) {
         const int ft = tile + p.prefetch_tiles;
         if (ft < p.n_tiles) {
-            const int fo = ft / p.tiles_per_outer;
+            const int fo = fast_div(ft, p.div_tpo_m, p.div_tpo_s);
             const int fi0 = (ft - fo * p.tiles_per_outer) * W;
-            const int fo1 = fo / p.n_o2, fo2 = fo - fo1 * p.n_o2;
+            const int fo1 = fast_div(fo, p.div_o2_m, p.div_o2_s), fo2 = fo - fo1 * p.n_o2;
             if (fi0 + W <= p.n_inner) {  // whole tiles only: never touch addresses past the array
                 const C *fin = reinterpret_cast<const C *>(p.in) + fo1 * p.in_os1 + fo2 * p.in_os2 + (long long)fi0 * p.in_is;
                 constexpr int ELT = (int)sizeof(C);
@@ -388,7 +429,7 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
         // ---- even/odd pre-pass: from the half spectrum X[0..L] of 2L reals build
         //   Z'[k] = (X[k] + conj X[L-k]) + i * conj(w_{2L}^k) * (X[k] - conj X[L-k])      ( = 2 Z[k] )
         // whose unnormalised inverse transform z has x[2j] = Re z[j], x[2j+1] = Im z[j]  (the launch always
-        // runs with the re/im swap on, i.e. as a backward transform).
+        // runs as a backward transform: conj here, forward butterflies, conj on store).
         const bool ok = (i0 + w1) < p.n_inner;
         T xl_re = (T)0;  // Re X[L], needed for k = 0 only
         if (u1 == 0 && ok) xl_re = ld_cplx<T>(gin + (long long)(i0 + w1) * p.in_is + (long long)L * p.in_ls).x;
@@ -413,7 +454,7 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
                 const C tt = cmul(csub(a, b), cconj(ld_cplx<T>(tw2 + k)));
                 zp = mk<T>(sum.x - tt.y, sum.y + tt.x);
             }
-            v[d] = mk<T>(zp.y, zp.x);  // swap: backward transform through the forward butterflies
+            v[d] = mk<T>(zp.x, -zp.y);  // conj: backward transform through the forward butterflies (tile_store conjugates back)
         }
         __syncthreads();  // every partner has been read before the stages overwrite shared memory
     }
@@ -568,32 +609,28 @@ fft_cluster_kernel(const TileParams p) {
     const int w = t & (W - 1), u = t >> LOG_W;
     const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);       // w_LL^k
     const C *__restrict__ twL = reinterpret_cast<const C *>(p.tw_aux);  // w_L^k
-    const bool inv = p.inverse != 0;
+    const unsigned cmask = p.inverse ? 0x80000000u : 0u;
 
     // every CTA of the cluster must be running before its shared memory is written remotely: arrive now,
     // wait just before the first scatter (the HBM loads in between hide the barrier)
     asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     bool first = true;
     for (int tile = (int)blockIdx.x / CL; tile < p.n_tiles; tile += n_clusters) {
-        const int o = tile / p.tiles_per_outer;
+        const int o = fast_div(tile, p.div_tpo_m, p.div_tpo_s);
         const int i0 = (tile - o * p.tiles_per_outer) * W;
-        const int o1 = o / p.n_o2, o2 = o - o1 * p.n_o2;
+        const int o1 = fast_div(o, p.div_o2_m, p.div_o2_s), o2 = o - o1 * p.n_o2;
         const C *__restrict__ gin = reinterpret_cast<const C *>(p.in) + o1 * p.in_os1 + o2 * p.in_os2;
         C v[R];
         // ---- A: HBM -> registers -> cross-CTA radix-CL stage -> owners' shared memory
         {
-            const bool ok = (i0 + w) < p.n_inner;
+            const int wi = min(i0 + w, p.n_inner - 1);  // ragged last tile: re-read the last valid line (never stored)
             const int j0 = c * (LL / CL) + u;
-            const C *src = gin + (long long)(i0 + w) * p.in_is + (long long)j0 * p.in_ls;
+            const C *src = gin + (long long)wi * p.in_is + (long long)j0 * p.in_ls;
 #pragma unroll
             for (int it = 0; it < NI; ++it)
 #pragma unroll
-                for (int d = 0; d < CL; ++d) {
-                    C x = mk<T>((T)0, (T)0);
-                    if (ok) x = ld_data<T>(src + (long long)(d * LL + it * T_LINE) * p.in_ls);
-                    if (inv) { T s = x.x; x.x = x.y; x.y = s; }
-                    v[it * CL + d] = x;
-                }
+                for (int d = 0; d < CL; ++d)
+                    v[it * CL + d] = conj_if(ld_data<T>(src + (long long)(d * LL + it * T_LINE) * p.in_ls), cmask);
             if (first) { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); first = false; }
 #pragma unroll
             for (int it = 0; it < NI; ++it) {

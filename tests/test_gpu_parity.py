@@ -616,6 +616,50 @@ def test_concurrent_plans_from_many_threads(L, oracle):
     assert all(e is None for e in errors), errors
 
 
+def test_destroy_racing_exec_is_safe(L, oracle):
+    """destroy_plan runs on a CPU processor while a GPU task may still be inside execute_plan on the same handle
+    (src/fft.rg:613-617 vs 624-645): every ABI call holds a reference for its duration, so the racing calls either
+    complete or report FFTB200_INVALID_PLAN — never a crash — and a later exec on the stale handle is refused."""
+    import threading
+    shape = (64, 64, 64)
+    x = torch.from_numpy(oracle.synth(shape, np.complex128, 950)).cuda()
+    y = torch.empty_like(x)
+    for round_ in range(20):
+        h = L.plan_many(3, list(shape), None, 0, 0, None, 0, 0, L.Z2Z, 1)
+        stop = threading.Event()
+        outcomes = []
+
+        def hammer():
+            lib = L.lib()
+            while not stop.is_set():
+                rc = lib.fftb200_exec_z2z(h, x.data_ptr(), y.data_ptr(), -1)
+                outcomes.append(rc)
+                buf = ctypes.create_string_buffer(4096)
+                outcomes.append(lib.fftb200_describe(h, buf, 4096))
+                if rc != 0:
+                    break
+
+        ts = [threading.Thread(target=hammer) for _ in range(3)]
+        for t in ts:
+            t.start()
+        while len(outcomes) < 10:
+            pass
+        L.destroy(h)
+        stop.set()
+        for t in ts:
+            t.join()
+        assert set(outcomes) <= {L.SUCCESS, L.INVALID_PLAN}, set(outcomes)
+        with pytest.raises(L.FFTB200Error):
+            L.execute(h, L.Z2Z, x.data_ptr(), y.data_ptr())
+    torch.cuda.synchronize()
+    want = cpu_fft(oracle, "z2z", x.cpu().numpy(), shape)
+    h = L.plan_many(3, list(shape), None, 0, 0, None, 0, 0, L.Z2Z, 1)
+    L.execute(h, L.Z2Z, x.data_ptr(), y.data_ptr())
+    torch.cuda.synchronize()
+    L.destroy(h)
+    assert oracle.rel_l2(y.cpu().numpy(), want) <= oracle.tolerance(64 ** 3, False)
+
+
 def test_host_memory_regions_are_staged(L, oracle):
     """The reference's mapper puts regions in zero-copy (pinned host) memory (test/test_mapper.cc:45-58):
     host pointers — pinned or pageable — go through the plan's HBM staging and give the same bits."""

@@ -74,6 +74,20 @@ __global__ void __launch_bounds__(512, MINB) ldg_copy(const double2 *__restrict_
     for (int d = 0; d < R; ++d) out[base + (long long)(u + d * 64) * g.ls + w] = v[d];
 }
 
+// narrower tiles: WW complex64 per row (64- or 32-byte row segments), 64 row slots, WW * 64 threads
+template <int R, int WW, int MINB>
+__global__ void __launch_bounds__(WW * 64, MINB) ldg_copy_narrow(const double2 *__restrict__ in, double2 *__restrict__ out, Geo g) {
+    const int t = threadIdx.x, w = t % WW, u = t / WW;
+    const long long tiles_x = g.n2 / WW;
+    const long long o = blockIdx.x / tiles_x, xb = blockIdx.x - o * tiles_x;
+    const long long base = (g.axis == 0 ? o * g.n2 : o * g.n1 * g.n2) + xb * WW;
+    double2 v[R];
+#pragma unroll
+    for (int d = 0; d < R; ++d) v[d] = __ldg(in + base + (long long)(u + d * 64) * g.ls + w);
+#pragma unroll
+    for (int d = 0; d < R; ++d) out[base + (long long)(u + d * 64) * g.ls + w] = v[d];
+}
+
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -279,6 +293,14 @@ int main(int argc, char **argv) {
         CK(cudaMemset(out, 0, n * 16));
         report("ldg tile R=16 1CTA/SM", time_ms([&] { ldg_copy<16, 1><<<(unsigned)g.n_tiles, 512>>>(in, out, g); }, reps));
         check(in, out, n, "ldg");
+    }
+    if (g.L == 1024) {
+        CK(cudaMemset(out, 0, n * 16));
+        report("ldg tile W=4 (64 B rows) R=16 2CTA/SM", time_ms([&] { ldg_copy_narrow<16, 4, 2><<<(unsigned)(g.n_tiles * 2), 256>>>(in, out, g); }, reps));
+        check(in, out, n, "ldg w4");
+        CK(cudaMemset(out, 0, n * 16));
+        report("ldg tile W=2 (32 B rows) R=16 4CTA/SM", time_ms([&] { ldg_copy_narrow<16, 2, 4><<<(unsigned)(g.n_tiles * 4), 128>>>(in, out, g); }, reps));
+        check(in, out, n, "ldg w2");
     }
     const unsigned tile_bytes = (unsigned)g.L * W * 16u;
     auto run_tma = [&](auto kern, int nbuf, int ctas_per_sm, const char *name) {
