@@ -441,9 +441,6 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> int:
     L = fft._lib
     L.lib()
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -696,9 +693,18 @@ def main() -> int:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    if args.impl == "reference":
-        return run_reference(args, rank)
-    return run_b200(args, rank, world, local_rank)
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner, for one) goes to
+    # stderr instead, and the line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
+    try:
+        if args.impl == "reference":
+            return run_reference(args, rank)
+        return run_b200(args, rank, world, local_rank)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":

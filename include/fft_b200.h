@@ -103,9 +103,19 @@ FFTB200_API int fftb200_exec_r2c(fftb200_handle plan, const void *in, void *out)
 FFTB200_API int fftb200_exec_d2z(fftb200_handle plan, const void *in, void *out);
 /* Unnormalised inverse of R2C / D2Z (cufftExecC2R / cufftExecZ2D, fftw_plan_dft_c2r semantics): in = packed half
  * spectrum [..][n_last/2+1] complex, out = [..][n_last] reals = n_total * the original data.  The input is
- * preserved (multi-dimensional plans go through a plan-owned work buffer).  Power-of-two sizes only. */
+ * preserved (multi-dimensional plans go through a plan-owned work buffer).  Power-of-two sizes only.
+ * In-place transforms (in == out): C2C / Z2Z whenever the two layouts coincide; R2C / D2Z with FFTW's padded in-place
+ * layout, i.e. input rows of 2*(n_last/2+1) reals (inembed[last] = 2*(n_last/2+1), onembed[last] = n_last/2+1,
+ * fftw-3.3.8/doc/reference.texi "Real-data DFT Array Format"), power-of-two sizes. */
 FFTB200_API int fftb200_exec_c2r(fftb200_handle plan, const void *in, void *out);
 FFTB200_API int fftb200_exec_z2d(fftb200_handle plan, const void *in, void *out);
+
+/* Normalisation helper.  Every transform here is unnormalised like FFTW's and cuFFT's (a forward transform followed
+ * by the backward one multiplies the data by n_total, fftw-3.3.8/doc/reference.texi:1982-2004); the reference has no
+ * backward path at all (src/fft.rg:319,574-580), so this has no call site there.  Scales, on the plan's stream and in
+ * place, exactly the elements the plan's transform WRITES (its output layout: advanced-layout padding is untouched) by
+ * `factor`; factor == 0 means 1 / n_total (n_total = product of n[], per batch member). */
+FFTB200_API int fftb200_scale(fftb200_handle plan, void *data, double factor);
 
 /* Free the plan's device tables and work buffers.  Any thread; no current device needed. */
 FFTB200_API int fftb200_destroy(fftb200_handle plan);

@@ -36,6 +36,7 @@ SYMBOLS = {
     "fftb200_exec_d2z": (ctypes.c_int, [_handle, _vp, _vp]),
     "fftb200_exec_c2r": (ctypes.c_int, [_handle, _vp, _vp]),
     "fftb200_exec_z2d": (ctypes.c_int, [_handle, _vp, _vp]),
+    "fftb200_scale": (ctypes.c_int, [_handle, _vp, ctypes.c_double]),
     "fftb200_destroy": (ctypes.c_int, [_handle]),
     "fftb200_get_work_size": (ctypes.c_int, [_handle, ctypes.POINTER(ctypes.c_ulonglong)]),
     "fftb200_get_launch_count": (ctypes.c_int, [_handle, _ip]),
@@ -124,6 +125,11 @@ def execute(h: int, ftype: int, in_ptr: int, out_ptr: int, direction: int = FORW
     else:
         raise ValueError("bad transform type")
     check(rc, "fftb200_exec")
+
+
+def scale(h: int, data_ptr: int, factor: float = 0.0) -> None:
+    """normalisation helper: scale the plan's output array in place (factor 0 = 1 / n_total)"""
+    check(lib().fftb200_scale(h, data_ptr, factor), "fftb200_scale")
 
 
 def destroy(h: int) -> None:

@@ -97,6 +97,13 @@ int fftb200_exec_z2d(fftb200_handle plan, const void *in, void *out) {
     return exec_typed(plan, in, out, FFTB200_INVERSE, FFTB200_Z2D);
 }
 
+int fftb200_scale(fftb200_handle plan, void *data, double factor) {
+    const std::shared_ptr<Plan> hold = lookup_plan(plan);
+    Plan *P = hold.get();
+    if (!P) return FFTB200_INVALID_PLAN;
+    return scale_plan(P, data, factor);
+}
+
 int fftb200_destroy(fftb200_handle plan) {
     if (plan == 0) return FFTB200_SUCCESS;  // zero-filled plan regions (src/fft.rg:523-531)
     const std::shared_ptr<Plan> hold = unregister_plan(plan);

@@ -75,6 +75,26 @@ __global__ void gen_scatter_kernel(const cplx<T> *__restrict__ packed, cplx<T> *
     }
 }
 
+// in-place scaling of the elements of a layout (normalisation helper); COMPONENTS = 2 for complex, 1 for real elements
+template <typename T, int COMPONENTS>
+__global__ void gen_scale_kernel(T *__restrict__ data, GenLayout lay, long long total, T factor) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        long long rem = e, off = 0;
+#pragma unroll
+        for (int d = 3; d >= 0; --d) {
+            if (d < lay.nd) {
+                const long long q = rem / lay.n[d];
+                off += (rem - q * lay.n[d]) * lay.stride[d];
+                rem = q;
+            }
+        }
+        T *q = data + COMPONENTS * off;
+#pragma unroll
+        for (int c = 0; c < COMPONENTS; ++c) q[c] *= factor;
+    }
+}
+
 // one radix-p stage along the middle index of packed [outer][L][inner]
 template <typename T>
 __global__ void gen_stage_kernel(const cplx<T> *__restrict__ x, cplx<T> *__restrict__ y,

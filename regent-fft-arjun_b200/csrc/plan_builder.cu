@@ -152,8 +152,13 @@ static const char *variant_name(int v) {
 // Add one tile pass.  levels: non-axis index levels, fastest first (levels[0] = lines of a tile).
 bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long long out_ls, std::vector<Level> lv,
                           int src, int dst, long long twN /* four-step N */, const char *what) {
+    return add_tile_pass_with(B, find_tile_kernel(B.P->prec, variant, L), variant, L, in_ls, out_ls, lv, src, dst, twN, what);
+}
+
+// same, with the kernel (tile shape) chosen by the caller
+bool add_tile_pass_with(Builder &B, const TileKernelInfo *ki, int variant, int L, long long in_ls, long long out_ls,
+                        std::vector<Level> lv, int src, int dst, long long twN, const char *what) {
     Plan *P = B.P;
-    const TileKernelInfo *ki = find_tile_kernel(P->prec, variant, L);
     if (!ki) return false;
     merge_levels(lv);
     if (lv.size() > 3) return false;
@@ -277,6 +282,19 @@ static std::vector<int> split_1d(long long N, int prec) {
     return f;
 }
 
+// in == out is allowed when the output layout occupies the input's addresses line by line: identical strides for complex
+// transforms; for real input FFTW's padded in-place format (rows of 2*(n_last/2+1) reals, i.e. every input stride,
+// counted in reals, is twice the output stride counted in complex).  Each pass loads its whole tile before it stores.
+static bool layouts_coincide(const Plan *P) {
+    const int rank = P->rank;
+    if (P->in_stride[rank] != 1 || P->out_stride[rank] != 1) return false;
+    for (int d = 0; d < rank; ++d) {
+        const long long want = P->real ? 2 * P->out_stride[d] : P->out_stride[d];
+        if ((d > 0 || P->batch > 1) && P->in_stride[d] != want) return false;
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // fast plan (power-of-two, unit element stride)
 // ------------------------------------------------------------------------------------------
@@ -380,32 +398,52 @@ static bool build_fast(Builder &B) {
     // layout.  Measured on B200: 512^3 fp64 last pass 0.833 -> 0.701 ms, middle pass 0.687 -> 0.711 ms, transform
     // 2.21 -> 2.10 ms.  Costs one work buffer of the transform's size; FFTB200_ZBLOCK=0 (or a failed allocation)
     // keeps the in-place three-pass plan.
-    if (env_int_or("FFTB200_ZBLOCK", 1) != 0 && rank == 3 && !P->real && P->batch == 1 && !first && n[0] > 1 && n[1] > 1) {
+    // Real transforms (n2c = n2/2+1 columns, not a multiple of the tile width) get the same layout with a ragged last
+    // column block, run as a separate small launch per pass (1024^3 D2Z last pass 4.70 -> see profiles/).
+    if (env_int_or("FFTB200_ZBLOCK", 1) != 0 && rank == 3 && P->batch == 1 && !first && n[0] > 1 && n[1] > 1) {
         const TileKernelInfo *k1 = find_tile_kernel(P->prec, V_CC, (int)n[1]);
         const TileKernelInfo *k0 = find_tile_kernel(P->prec, V_CC, (int)n[0]);
         const size_t ce = P->prec ? 16 : 8;
-        const bool dense = P->out_stride[3] == 1 && P->out_stride[2] == n[2] && P->out_stride[1] == n[1] * n[2];
-        const bool far = (size_t)(n[1] * n[2]) * ce >= (256u << 10);
+        const long long nx = nout[2];
+        const bool dense = P->out_stride[3] == 1 && P->out_stride[2] == nx && P->out_stride[1] == n[1] * nx;
+        const bool far = (size_t)(n[1] * nx) * ce >= (256u << 10);
         // (single-CTA tiles only.  1024^3 fp64, one 128 KiB tile per CTA: last pass 9.27 -> 7.09 ms, middle pass unchanged)
         const bool single = k1 && k0 && k1->cluster == 1 && k0->cluster == 1;
-        if (single && k1->W == k0->W && dense && far && n[2] % k1->W == 0) {
-            const long long Wt = k1->W, nxb = n[2] / Wt;
+        if (single && k1->W == k0->W && dense && far && nx >= k1->W) {
+            const long long Wt = k1->W, nxb_full = nx / Wt, rag = nx - nxb_full * Wt, nxb = nxb_full + (rag ? 1 : 0);
+            const size_t wbytes = (size_t)(n[0] * n[1] * nxb * Wt) * ce;
             void *w = nullptr;
-            if (cudaMalloc(&w, (size_t)(n[0] * n[1] * n[2]) * ce) == cudaSuccess) {
+            if (cudaMalloc(&w, wbytes) == cudaSuccess) {
                 P->dev_allocs.push_back(w);
                 P->work[0] = w;
-                P->work_bytes = (size_t)(n[0] * n[1] * n[2]) * ce;
+                P->work_bytes = wbytes;
                 // W element (z, y, x) at ((y * nxb + x / Wt) * n0 + z) * Wt + x % Wt
                 const long long w_y = nxb * n[0] * Wt, w_xb = n[0] * Wt, w_z = Wt;
-                std::vector<Level> lv1 = {{Wt, 1, 1}, {nxb, Wt, w_xb}, {n[0], P->out_stride[1], w_z}};
-                std::vector<Level> lv0 = {{Wt, 1, 1}, {nxb, w_xb, Wt}, {n[1], w_y, P->out_stride[2]}};
-                if (add_tile_pass(B, V_CC, (int)n[1], P->out_stride[2], w_y, lv1, BUF_OUT, BUF_WORK0, 0,
-                                  "strided axis -> blocked work buffer") &&
-                    add_tile_pass(B, V_CC, (int)n[0], w_z, P->out_stride[1], lv0, BUF_WORK0, BUF_OUT, 0,
-                                  "blocked work buffer -> strided axis")) {
-                    bool same_io = true;
-                    for (int d = 0; d <= rank; ++d) same_io = same_io && (P->in_stride[d] == P->out_stride[d]);
-                    P->inplace_ok = same_io;  // pass 1 is tile-wise in place, the others go through the work buffer
+                bool ok = true;
+                {   // middle axis: natural layout -> blocked work buffer
+                    std::vector<Level> lv1 = {{Wt, 1, 1}, {nxb_full, Wt, w_xb}, {n[0], P->out_stride[1], w_z}};
+                    ok = ok && add_tile_pass(B, V_CC, (int)n[1], P->out_stride[2], w_y, lv1, BUF_OUT, BUF_WORK0, 0,
+                                             "strided axis -> blocked work buffer");
+                    if (ok && rag) {
+                        std::vector<Level> lvr = {{rag, 1, 1}, {n[0], P->out_stride[1], w_z}};
+                        ok = add_tile_pass(B, V_CC, (int)n[1], P->out_stride[2], w_y, lvr, BUF_OUT, BUF_WORK0, 0,
+                                           "strided axis -> blocked work buffer (ragged last column block)");
+                        if (ok) { P->launches.back().in_off = nxb_full * Wt; P->launches.back().out_off = nxb_full * w_xb; }
+                    }
+                }
+                if (ok) {   // slowest axis: blocked work buffer (every tile one contiguous run) -> natural layout
+                    std::vector<Level> lv0 = {{Wt, 1, 1}, {nxb_full, w_xb, Wt}, {n[1], w_y, P->out_stride[2]}};
+                    ok = add_tile_pass(B, V_CC, (int)n[0], w_z, P->out_stride[1], lv0, BUF_WORK0, BUF_OUT, 0,
+                                       "blocked work buffer -> strided axis");
+                    if (ok && rag) {
+                        std::vector<Level> lvr = {{rag, 1, 1}, {n[1], w_y, P->out_stride[2]}};
+                        ok = add_tile_pass(B, V_CC, (int)n[0], w_z, P->out_stride[1], lvr, BUF_WORK0, BUF_OUT, 0,
+                                           "blocked work buffer -> strided axis (ragged last column block)");
+                        if (ok) { P->launches.back().in_off = nxb_full * w_xb; P->launches.back().out_off = nxb_full * Wt; }
+                    }
+                }
+                if (ok) {
+                    P->inplace_ok = layouts_coincide(P);  // pass 1 is tile-wise in place, the others go through the work buffer
                     return true;
                 }
                 return false;  // (the caller discards the partial plan and its allocations)
@@ -427,9 +465,7 @@ static bool build_fast(Builder &B) {
     }
     if (first) return false;
     // in place is safe when every pass reads and writes the same addresses tile by tile
-    bool same = !P->real;
-    for (int d = 0; d <= rank; ++d) same = same && (P->in_stride[d] == P->out_stride[d]);
-    P->inplace_ok = same;
+    P->inplace_ok = layouts_coincide(P);
     return true;
 }
 

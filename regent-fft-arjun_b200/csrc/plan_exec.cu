@@ -158,8 +158,9 @@ static int run_launches(Plan *P, const void *in, void *out, int inverse) {
         cudaError_t ce;
         if (ln.kind == Launch::TILE) {
             TileParams tp = ln.tp;
-            tp.in = src;
-            tp.out = dst;
+            const size_t elt = P->prec ? 16 : 8;  // launch offsets are in complex elements
+            tp.in = (const char *)src + (size_t)ln.in_off * elt;
+            tp.out = (char *)dst + (size_t)ln.out_off * elt;
             tp.inverse = inverse;
             tp.ticket = ln.ticket;
             ce = launch_tile(ln.ki, ln.grid, P->stream, tp);
@@ -218,6 +219,39 @@ int exec_plan(Plan *P, const void *in, void *out, int direction) {
         return FFTB200_EXEC_FAILED;
     }
     return FFTB200_SUCCESS;
+}
+
+// normalisation helper: scales the plan's output layout in place (include/fft_b200.h: fftb200_scale)
+int scale_plan(Plan *P, void *data, double factor) {
+    if (!data) return FFTB200_INVALID_VALUE;
+    if (P->slab) return FFTB200_UNSUPPORTED;
+    if (is_host_memory(data)) return FFTB200_INVALID_VALUE;  // device arrays only
+    DeviceGuard g(P->device);
+    std::lock_guard<std::mutex> lk(P->mu);
+    GenLayout lay{};
+    lay.nd = P->rank + 1;
+    lay.n[0] = P->batch;
+    lay.stride[0] = P->out_stride[0];
+    long long total = P->batch, n_total = 1;
+    for (int d = 0; d < P->rank; ++d) {
+        const long long no = (P->real && d == P->rank - 1) ? P->n[d] / 2 + 1 : P->n[d];
+        lay.n[d + 1] = no;
+        lay.stride[d + 1] = P->out_stride[d + 1];
+        total *= no;
+        n_total *= P->n[d];
+    }
+    const double f = factor != 0.0 ? factor : 1.0 / (double)n_total;
+    long long gl = (total + 255) / 256;
+    if (gl > 148ll * 64) gl = 148ll * 64;
+    const unsigned grid = (unsigned)(gl < 1 ? 1 : gl);
+    if (P->prec) {
+        if (P->c2r) gen_scale_kernel<double, 1><<<grid, 256, 0, P->stream>>>((double *)data, lay, total, f);
+        else gen_scale_kernel<double, 2><<<grid, 256, 0, P->stream>>>((double *)data, lay, total, f);
+    } else {
+        if (P->c2r) gen_scale_kernel<float, 1><<<grid, 256, 0, P->stream>>>((float *)data, lay, total, (float)f);
+        else gen_scale_kernel<float, 2><<<grid, 256, 0, P->stream>>>((float *)data, lay, total, (float)f);
+    }
+    return cudaGetLastError() == cudaSuccess ? FFTB200_SUCCESS : FFTB200_EXEC_FAILED;
 }
 
 static int exec_fallback(Plan *P, const void *in, void *out, int direction) {

@@ -95,6 +95,7 @@ struct DeviceGuard {
 cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st, const TileParams &tp);
 void free_plan_resources(Plan *p);
 int exec_plan(Plan *P, const void *in, void *out, int direction);
+int scale_plan(Plan *P, void *data, double factor);
 // handle table: handle = (generation << 32) | (slot + 1); never a raw pointer
 // the table owns the plan; ABI calls hold a shared_ptr for their duration (destroy racing exec is safe)
 fftb200_handle register_plan(Plan *p);
@@ -123,6 +124,8 @@ struct Builder {
 // Add one tile pass.  levels: non-axis index levels, fastest first (levels[0] = lines of a tile).
 bool add_tile_pass(Builder &B, int variant, int L, long long in_ls, long long out_ls, std::vector<Level> lv, int src, int dst,
                    long long twN /* four-step N */, const char *what);
+bool add_tile_pass_with(Builder &B, const TileKernelInfo *ki, int variant, int L, long long in_ls, long long out_ls,
+                        std::vector<Level> lv, int src, int dst, long long twN, const char *what);
 int create_plan(Plan **out, int rank, const long long *n, int batch, const long long *in_stride, const long long *out_stride,
                 fftb200_type type, bool force_generic);
 

@@ -30,6 +30,7 @@
 #include <cstring>
 
 #include "plan_internal.h"
+#include "slab_fused_kernel.cuh"
 
 namespace fftb200 {
 
@@ -61,6 +62,12 @@ struct SlabState {
     // global transpose into the peers' receive slabs, hand-shake, row FFT over the received (now contiguous) n0
     bool two_d = false;
     int l_2a = -1, l_2b = -1;
+    // complex cubes: the whole transform as ONE persistent kernel per rank (slab_fused_kernel.cuh)
+    const SlabFusedKernelInfo *fused = nullptr;
+    TileKernelInfo fused_ki{};          // the fused kernel's tile shape, for the pass builder
+    int l_fy = -1, l_fx = -1, l_fz = -1;
+    unsigned *fused_counters = nullptr;
+    unsigned fused_grid = 0;
 };
 
 // flags: [kind 0 = "receive buffer free", 1.. = "chunk j written"][source rank] epochs
@@ -326,6 +333,55 @@ int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, in
                 return fail(B.err ? B.err : FFTB200_UNSUPPORTED);
             S->l_z = (int)P->launches.size() - 1;
         }
+        // ---- the same three passes for the fused single-kernel path (cubes whose side has a fused kernel):
+        // y over ALL local planes, x over one chunk's rows (the kernel adds the chunk shift), z over everything
+        const SlabFusedKernelInfo *fk = (S->n0 == S->n1 && S->n1 == S->n2) ? find_slab_fused_kernel(P->prec, (int)S->n0) : nullptr;
+        if (fk && env_int_or("FFTB200_SLAB_FUSED", 1) != 0 && pc >= fk->W && S->n2p == S->n2) {
+            S->fused_ki = TileKernelInfo{reinterpret_cast<void (*)(const TileParams)>(fk->fn), fk->L, fk->R, fk->W, fk->threads,
+                                         fk->smem_bytes, 1};
+            bool ok = true;
+            {
+                std::vector<Level> lv = {{S->n2, 1, 1}, {S->n0l, S->n1 * S->n2, S->n2p}};
+                ok = ok && add_tile_pass_with(B, &S->fused_ki, V_CC_PEER, (int)S->n1, S->n2, S->n0 * S->n2p, lv, BUF_IN, BUF_OUT, 0,
+                                              "fused slab kernel: y axis, store = exchange (peer memory)");
+                if (ok) {
+                    Launch &ln = P->launches.back();
+                    ln.out_off = (long long)rank * S->n0l * S->n2p;
+                    set_peer(ln);
+                    S->l_fy = (int)P->launches.size() - 1;
+                }
+            }
+            if (ok) {
+                std::vector<Level> lv = {{pc, S->n2p, S->n2p}, {(long long)G, S->n0l * S->n2p, S->n0l * S->n2p},
+                                         {S->n1l, S->n0 * S->n2p, S->n0 * S->n2p}};
+                ok = add_tile_pass_with(B, &S->fused_ki, V_RR, (int)S->n2, 1, 1, lv, BUF_WORK1, BUF_WORK1, 0,
+                                        "fused slab kernel: x axis on the received planes of one chunk");
+                if (ok) S->l_fx = (int)P->launches.size() - 1;
+            }
+            if (ok) {
+                std::vector<Level> lv = {{S->n2, 1, 1}, {S->n1l, S->n0 * S->n2p, S->n0 * S->n2c}};
+                ok = add_tile_pass_with(B, &S->fused_ki, V_CC, (int)S->n0, S->n2p, S->n2c, lv, BUF_WORK1, BUF_OUT, 0,
+                                        "fused slab kernel: z axis");
+                if (ok) S->l_fz = (int)P->launches.size() - 1;
+            }
+            if (ok) {
+                S->fused_counters = (unsigned *)B.alloc(sizeof(unsigned) * (size_t)(2 + S->Jp));
+                int sms = 148, per_sm = 1;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P->device);
+                if (fk->smem_bytes > 48 * 1024)
+                    cudaFuncSetAttribute((const void *)fk->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fk->smem_bytes);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fk->fn, fk->threads, fk->smem_bytes) != cudaSuccess ||
+                    per_sm < 1)
+                    per_sm = 1;
+                cudaGetLastError();
+                const long long total = (long long)S->Jp * (P->launches[S->l_fy].tp.n_tiles / S->Jp + P->launches[S->l_fx].tp.n_tiles) +
+                                        P->launches[S->l_fz].tp.n_tiles;
+                S->fused_grid = (unsigned)std::min<long long>(total, (long long)sms * per_sm);
+                for (int l : {S->l_fy, S->l_fx, S->l_fz}) P->launches[l].tp.prefetch_tiles = 0;
+                if (S->fused_counters && B.err == FFTB200_SUCCESS) S->fused = fk;
+            }
+            if (!S->fused && B.err != FFTB200_SUCCESS) return fail(B.err);
+        }
     }
     if (cudaStreamCreateWithFlags(&S->aux, cudaStreamNonBlocking) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
     S->ev_chunk.assign(std::max(S->J, S->Jp), nullptr);
@@ -416,8 +472,8 @@ static int slab_exec_p2p_body(Plan *P, const void *in, void *out, int inverse, c
     cudaStream_t st = P->stream;
     const unsigned long long *myflags = slab_flags(S, S->rank);
     if (S->timing) cudaEventRecord(S->ev_t[0], st);
-    // my receive buffer is free again (stream order: after my previous transform's pass 3)
-    if (S->G > 1) slab_signal_kernel<<<1, 32, 0, st>>>(peers, S->G, S->rank, 0, epoch);
+    // my receive buffer is free again (stream order: after my previous transform's pass 3); the fused kernel says so itself
+    if (S->G > 1 && !(S->fused && !P->real)) slab_signal_kernel<<<1, 32, 0, st>>>(peers, S->G, S->rank, 0, epoch);
     if (S->two_d) {
         if (S->G > 1) slab_wait_kernel<<<1, 32, 0, st>>>(myflags, S->G, 0, epoch, S->err_host);
         if (S->timing) cudaEventRecord(S->ev_t[1], st);
@@ -431,6 +487,41 @@ static int slab_exec_p2p_body(Plan *P, const void *in, void *out, int inverse, c
         rc2 = slab_launch(P, S->l_2b, S->area, out, nullptr, inverse, st);
         if (rc2) return rc2;
         if (S->timing) cudaEventRecord(S->ev_t[3], st);
+        return cudaGetLastError() == cudaSuccess ? FFTB200_SUCCESS : FFTB200_EXEC_FAILED;
+    }
+    if (!P->real && S->fused) {
+        // one persistent kernel: y axis + exchange, hand-shakes, x axis on arrived chunks, z axis
+        const size_t ce = P->prec ? 16 : 8;
+        SlabFusedParams fp;
+        const Launch &ly = P->launches[S->l_fy], &lx = P->launches[S->l_fx], &lz = P->launches[S->l_fz];
+        fp.y = ly.tp;
+        fp.y.in = in;
+        fp.y.out = nullptr;
+        fp.y.inverse = inverse;
+        for (int d = 0; d < S->G; ++d) fp.y.peer[d] = (char *)recv[d] + (size_t)ly.out_off * ce;
+        fp.x = lx.tp;
+        fp.x.in = S->area;
+        fp.x.out = S->area;
+        fp.x.inverse = inverse;
+        fp.z = lz.tp;
+        fp.z.in = S->area;
+        fp.z.out = out;
+        fp.z.inverse = inverse;
+        fp.counters = S->fused_counters;
+        for (int d = 0; d < MAX_PEERS; ++d) fp.flags[d] = peers.flags[d];
+        fp.err = S->err_host;
+        fp.epoch = epoch;
+        fp.x_chunk_shift = (S->n0l / S->Jp) * S->n2p;
+        fp.G = S->G;
+        fp.me = S->rank;
+        fp.n_chunks = S->Jp;
+        fp.tiles_y_chunk = ly.tp.n_tiles / S->Jp;
+        fp.tiles_x_chunk = lx.tp.n_tiles;
+        fp.tiles_z = lz.tp.n_tiles;
+        if (cudaMemsetAsync(S->fused_counters, 0, sizeof(unsigned) * (size_t)(2 + S->Jp), st) != cudaSuccess) return FFTB200_EXEC_FAILED;
+        if (S->timing) cudaEventRecord(S->ev_t[1], st);
+        S->fused->fn<<<S->fused_grid, S->fused->threads, S->fused->smem_bytes, st>>>(fp);
+        if (S->timing) { cudaEventRecord(S->ev_t[2], st); cudaEventRecord(S->ev_t[3], st); }
         return cudaGetLastError() == cudaSuccess ? FFTB200_SUCCESS : FFTB200_EXEC_FAILED;
     }
     if (!P->real) {
@@ -608,6 +699,7 @@ int slab_get_phase_ms(Plan *P, float *ms) {
 int slab_launches_per_exec(const Plan *P) {
     const SlabState *S = P->slab;
     if (S->two_d) return 2 + (S->G > 1 ? 4 : 0);
+    if (S->fused && !P->real) return 1;
     const int J = P->real ? S->J : S->Jp;
     return 1 + 2 * J + (S->G > 1 ? 2 + 2 * J : 0);
 }

@@ -157,6 +157,9 @@ __device__ __forceinline__ float2 conj_if(float2 x, unsigned mask) {
 // ld.global.nc.L1::no_allocate were measured on B200 and made the 512^3 passes 5-10 % slower / no different,
 // so tile data uses the default policies (DESIGN.md "Experiments").
 template <typename T> __device__ __forceinline__ cplx<T> ld_data(const cplx<T> *p) { return __ldg(p); }
+// L2-coherent load (ld.global.cg): for tile data that other SMs or peer GPUs wrote earlier in the SAME kernel (the fused
+// slab kernel); the read-only / L1 path could return lines cached before that write
+template <typename T> __device__ __forceinline__ cplx<T> ld_data_cg(const cplx<T> *p) { return __ldcg(p); }
 template <typename T> __device__ __forceinline__ void st_data(cplx<T> *p, cplx<T> v) { *p = v; }
 
 // ---------------------------------------------------------------------------------------------
@@ -258,7 +261,8 @@ __device__ __forceinline__ void tile_stages(cplx<T> *v, cplx<T> *sm, const cplx<
 // ---------------------------------------------------------------------------------------------
 template <typename T, int L, int R, int W, int VAR>
 __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p, const int o1, const int o2, const int i0,
-                                           const int wl, const int ul, const int kmul, const int kadd) {
+                                           const int wl, const int ul, const int kmul, const int kadd,
+                                           const long long out_shift = 0) {
     using TR = TileTraits<T, L, R, W, VAR>;
     using C = cplx<T>;
     constexpr int S = TR::S;
@@ -267,7 +271,7 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
     constexpr int RL = (S > 1) ? TR::R_LAST : R;
     const unsigned cmask = p.inverse ? 0x80000000u : 0u;
     const bool ok = (i0 + wl) < p.n_inner;
-    const long long off = o1 * p.out_os1 + o2 * p.out_os2 + (long long)(i0 + wl) * p.out_is;
+    const long long off = o1 * p.out_os1 + o2 * p.out_os2 + (long long)(i0 + wl) * p.out_is + out_shift;
     C *dst = reinterpret_cast<C *>(p.out) + off;
     if constexpr (VAR == V_CC_TW) {
         // four-step twiddles by recurrence in fp64: the exponent of w_N is affine in (b, q),
@@ -308,9 +312,15 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
 #pragma unroll
             for (int q = 0; q < RL; ++q) {
                 C x = v[b * RL + q];
-                const double xr = (double)x.x * wq.x - (double)x.y * wq.y;
-                const double xi = (double)x.x * wq.y + (double)x.y * wq.x;
-                x.x = (T)xr; x.y = (T)xi;
+                if constexpr (sizeof(T) == 4) {
+                    // fp32 data: the twiddle is carried in fp64 (recurrence) and rounded once to fp32 for the multiply;
+                    // converting the data to fp64 and back instead costs four conversions per point on a slow pipe
+                    x = cmul(x, mk<T>((T)wq.x, (T)wq.y));
+                } else {
+                    const double xr = (double)x.x * wq.x - (double)x.y * wq.y;
+                    const double xi = (double)x.x * wq.y + (double)x.y * wq.x;
+                    x.x = (T)xr; x.y = (T)xi;
+                }
                 x = conj_if(x, cmask);
                 if (ok) st_data<T>(pq, x);
                 pq += step_q;
@@ -350,8 +360,11 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
     }
 }
 
-template <typename T, int L, int R, int W, int VAR>
-__device__ __forceinline__ void fft_tile_body(const TileParams &p, const int tile, unsigned char *smem_raw) {
+// DATA_CG: tile data is read with ld.global.cg (see ld_data_cg).  in_shift / out_shift: element offsets added to the
+// pass's input / output addresses (chunked passes of the fused slab kernel).
+template <typename T, int L, int R, int W, int VAR, bool DATA_CG = false>
+__device__ __forceinline__ void fft_tile_body(const TileParams &p, const int tile, unsigned char *smem_raw,
+                                              const long long in_shift = 0, const long long out_shift = 0) {
     using TR = TileTraits<T, L, R, W, VAR>;
     using C = cplx<T>;
     constexpr int S = TR::S;
@@ -370,8 +383,8 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
     const int o = fast_div(tile, p.div_tpo_m, p.div_tpo_s);
     const int i0 = (tile - o * p.tiles_per_outer) * W;
     const int o1 = fast_div(o, p.div_o2_m, p.div_o2_s), o2 = o - o1 * p.n_o2;
-    const C *__restrict__ gin = reinterpret_cast<const C *>(p.in) + o1 * p.in_os1 + o2 * p.in_os2;
-    C *__restrict__ gout = reinterpret_cast<C *>(p.out) + o1 * p.out_os1 + o2 * p.out_os2;
+    const C *__restrict__ gin = reinterpret_cast<const C *>(p.in) + o1 * p.in_os1 + o2 * p.in_os2 + in_shift;
+    C *__restrict__ gout = reinterpret_cast<C *>(p.out) + o1 * p.out_os1 + o2 * p.out_os2 + out_shift;
     const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);
     const unsigned cmask = (p.inverse && VAR != V_RR_C2R) ? 0x80000000u : 0u;
 
@@ -388,7 +401,8 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
         const long long step = (long long)T_LINE * p.in_ls;
 #pragma unroll
         for (int d = 0; d < R; ++d) {
-            v[d] = conj_if(ld_data<T>(src), cmask);
+            if constexpr (DATA_CG) v[d] = conj_if(ld_data_cg<T>(src), cmask);
+            else v[d] = conj_if(ld_data<T>(src), cmask);
             src += step;
         }
     }
@@ -505,7 +519,7 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
             }
         }
     } else {
-        tile_store<T, L, R, W, VAR>(v, p, o1, o2, i0, wl, ul, 1, 0);
+        tile_store<T, L, R, W, VAR>(v, p, o1, o2, i0, wl, ul, 1, 0, out_shift);
     }
 }
 

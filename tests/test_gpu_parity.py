@@ -806,6 +806,81 @@ def test_inverse_real_transforms(L, oracle):
     assert lib.fftb200_plan_many(ctypes.byref(hbad), 1, n3, None, 0, 0, None, 0, 0, L.Z2D, 1) == L.UNSUPPORTED   # not 2^k
 
 
+def test_inplace_r2c_padded_layout(L, oracle):
+    """In-place R2C / D2Z with FFTW's padded format (rows of 2*(n/2+1) reals; fftw-3.3.8/doc/reference.texi, "Real-data
+    DFT Array Format"): the half spectrum overwrites the real rows it came from.  1-D, 2-D, 3-D (the 3-D case also takes
+    the blocked intermediate layout when its slowest stride is far)."""
+    for kind, shape in [("d2z", (4096,)), ("d2z", (64, 128)), ("r2c", (32, 64, 256)), ("d2z", (128, 128, 256)), ("d2z", (16, 8192))]:
+        ftype, dt_in, dt_out = _kinds(L)[kind]
+        nl = shape[-1]
+        nc = nl // 2 + 1
+        x = oracle.synth(shape, dt_in, 970 + len(shape))
+        pad = np.zeros(shape[:-1] + (2 * nc,), dtype=dt_in)
+        pad[..., :nl] = x
+        buf = torch.from_numpy(pad).cuda()
+        inembed = list(shape[:-1]) + [2 * nc]
+        onembed = list(shape[:-1]) + [nc]
+        h = L.plan_many(len(shape), list(shape), inembed, 1, int(np.prod(inembed)), onembed, 1, int(np.prod(onembed)), ftype, 1)
+        L.execute(h, ftype, buf.data_ptr(), buf.data_ptr())
+        torch.cuda.synchronize()
+        L.destroy(h)
+        got = buf.cpu().numpy().view(dt_out).reshape(shape[:-1] + (nc,))
+        want = cpu_fft(oracle, kind, x, shape)
+        err = oracle.rel_l2(got, want)
+        assert err <= oracle.tolerance(int(np.prod(shape)), kind == "r2c"), (kind, shape, err)
+    # an unpadded real layout cannot run in place: refused, not corrupted
+    h = L.plan_many(1, [256], None, 0, 0, None, 0, 0, L.D2Z, 1)
+    b = torch.zeros(258, dtype=torch.float64, device="cuda")
+    h2 = L.plan_many(2, [8, 256], None, 0, 0, None, 0, 0, L.D2Z, 1)
+    b2 = torch.zeros(8 * 258, dtype=torch.float64, device="cuda")
+    with pytest.raises(L.FFTB200Error):
+        L.execute(h2, L.D2Z, b2.data_ptr(), b2.data_ptr())
+    L.destroy(h)
+    L.destroy(h2)
+
+
+def test_normalisation_helper_round_trips(L, oracle):
+    """fftb200_scale: forward, backward, scale by 1/N gives the input back (FFTW leaves this to the user,
+    doc/reference.texi:1982-2004); advanced-layout padding is not touched; explicit factors work; C2R output scales."""
+    for kind, shape in [("z2z", (64, 32, 16)), ("c2c", (4096,)), ("z2z", (12, 10))]:
+        ftype, dt_in, _ = _kinds(L)[kind]
+        x = torch.from_numpy(oracle.synth(shape, dt_in, 980)).cuda()
+        y = torch.empty_like(x)
+        z = torch.empty_like(x)
+        h = L.plan_many(len(shape), list(shape), None, 0, 0, None, 0, 0, ftype, 1)
+        L.execute(h, ftype, x.data_ptr(), y.data_ptr(), -1)
+        L.execute(h, ftype, y.data_ptr(), z.data_ptr(), +1)
+        L.scale(h, z.data_ptr())
+        torch.cuda.synchronize()
+        L.destroy(h)
+        assert _rel(z, x) <= 2 * oracle.tolerance(int(np.prod(shape)), kind == "c2c"), (kind, shape)
+    # padded output rows: only the transform's own elements are scaled
+    n, pitch = 64, 80
+    h = L.plan_many(1, [n], [n], 1, n, [pitch], 1, pitch, L.Z2Z, 4)
+    x = torch.from_numpy(oracle.synth((4, n), np.complex128, 981)).cuda()
+    out = torch.full((4, pitch), 7.0 + 7.0j, dtype=torch.complex128, device="cuda")
+    L.execute(h, L.Z2Z, x.data_ptr(), out.data_ptr())
+    ref = out.clone()
+    L.scale(h, out.data_ptr(), 0.5)
+    torch.cuda.synchronize()
+    L.destroy(h)
+    assert torch.equal(out[:, :n], ref[:, :n] * 0.5) and torch.equal(out[:, n:], ref[:, n:])
+    # real round trip: D2Z then Z2D then scale
+    shape = (32, 64)
+    xr = torch.from_numpy(oracle.synth(shape, np.float64, 982)).cuda()
+    spec = torch.empty((32, 33), dtype=torch.complex128, device="cuda")
+    back = torch.empty_like(xr)
+    hf = L.plan_many(2, list(shape), None, 0, 0, None, 0, 0, L.D2Z, 1)
+    hb = L.plan_many(2, list(shape), None, 0, 0, None, 0, 0, L.Z2D, 1)
+    L.execute(hf, L.D2Z, xr.data_ptr(), spec.data_ptr())
+    L.execute(hb, L.Z2D, spec.data_ptr(), back.data_ptr())
+    L.scale(hb, back.data_ptr())
+    torch.cuda.synchronize()
+    L.destroy(hf)
+    L.destroy(hb)
+    assert _rel(back, xr) <= 2 * oracle.tolerance(32 * 64, False)
+
+
 def test_blocked_intermediate_layout_matches_in_place_plan(L, oracle, monkeypatch):
     """3-D complex plans with a far slowest-axis stride route the middle pass through a blocked work buffer; the
     result is bit-identical to the in-place three-pass plan (FFTB200_ZBLOCK=0), also in place and backward."""

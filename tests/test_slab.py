@@ -131,6 +131,36 @@ def test_slab_fused_single_rank_plane_chunks(fft, oracle, kind, planes, monkeypa
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kind,side,planes", [("z2z", 128, 4), ("z2z", 128, 1), ("c2c", 128, 8), ("z2z", 256, 4), ("c2c", 256, 2)])
+def test_slab_single_kernel_cubes_single_rank(fft, oracle, kind, side, planes, monkeypatch):
+    """complex cubes run the whole slab transform as ONE persistent kernel (tickets: y chunks, x chunks as they
+    'arrive', z); with one rank the hand-shake flags are the rank's own.  Also in place-safe reuse and the multi-launch
+    path (FFTB200_SLAB_FUSED=0) giving the same bits."""
+    from regent_fft_arjun_b200 import distributed as D
+    monkeypatch.setenv("FFTB200_SLAB_PLANE_CHUNKS", str(planes))
+    dt = {"z2z": fft.complex64, "c2c": fft.complex32}[kind]
+    np_in = {"z2z": np.complex128, "c2c": np.complex64}[kind]
+    shape = (side, side, side)
+    x = oracle.synth(shape, np_in, seed=93)
+    xd = torch.from_numpy(x).cuda()
+    outs = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("FFTB200_SLAB_FUSED", fused)
+        plan = D.SlabFFT3D(shape, dt, rank=0, world=1, device="cuda:0", mode="p2p")
+        assert (fft._lib.launch_count(plan.engine.h) == 1) == (fused == "1")
+        for _ in range(3):
+            plan.execute(xd)
+        torch.cuda.synchronize()
+        outs.append(plan.out.clone())
+        got = plan.gather_natural()
+        plan.destroy()
+        assert np.array_equal(xd.cpu().numpy(), x)
+        want = oracle.FFTW.get("ref").dft(x.astype(np.complex128)) if oracle.have_fftw("ref") else oracle.port_dft(x.astype(np.complex128))
+        assert oracle.rel_l2(got, want) <= oracle.tolerance(int(np.prod(shape)), kind == "c2c"), (kind, side, fused)
+    assert torch.equal(outs[0], outs[1]), "single-kernel and multi-launch paths differ"
+
+
+@pytest.mark.gpu
 def test_slab_2d_single_rank(fft, oracle):
     """2-D slab plan with G = 1: row pass into the (local) receive slab transposed, row pass back"""
     from regent_fft_arjun_b200 import distributed as D
@@ -167,6 +197,8 @@ def test_slab_multi_gpu(built, mode):
     if n < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
     world = 2 if n < 4 else 4
-    for kind, shape in [("z2z", "64,64,64"), ("d2z", "32,64,128"), ("c2c", "128,128,64")]:
+    # (the 128^3 and 256^3 complex cubes take the single-kernel path in p2p mode: slab_fused_kernel.cuh)
+    for kind, shape in [("z2z", "64,64,64"), ("d2z", "32,64,128"), ("c2c", "128,128,64"), ("z2z", "128,128,128"),
+                        ("c2c", "256,256,256")]:
         _torchrun(world, ["--backend", "nccl", "--engine", "cuda", "--mode", mode, "--kind", kind, "--shape", shape,
                           "--chunks", "4", "--reps", "3"], port=29800 + (7 if mode == "p2p" else 0) + len(shape))
