@@ -115,7 +115,7 @@ int fftb200_get_work_size(fftb200_handle plan, unsigned long long *bytes) {
     const std::shared_ptr<Plan> hold = lookup_plan(plan);
     Plan *P = hold.get();
     if (!P || !bytes) return P ? FFTB200_INVALID_VALUE : FFTB200_INVALID_PLAN;
-    *bytes = (unsigned long long)P->work_bytes * ((P->work[0] ? 1 : 0) + (P->work[1] ? 1 : 0));
+    *bytes = (unsigned long long)P->work_bytes * ((P->work[0] ? 1 : 0) + (P->work[1] ? 1 : 0)) + P->blu_bytes;
     return FFTB200_SUCCESS;
 }
 

@@ -131,6 +131,61 @@ __global__ void gen_stage_kernel(const cplx<T> *__restrict__ x, cplx<T> *__restr
     }
 }
 
+// ---- Bluestein (chirp-z) for lengths with a large prime factor: a length-L DFT as a cyclic convolution of length
+// M = 2^m >= 2L-1 (fftw-3.3.8/dft/bluestein.c does the same on the CPU path).  With c[j] = exp(-i*pi*j^2/L):
+//   X[k] = c[k] * sum_j (x[j] c[j]) * conj(c[k-j])
+// pre:  a[o][j][i] = x[o][j][i] * c[j] (j < L), 0 (L <= j < M);  then FFT_M, times Bhat = FFT_M(conj chirp, wrapped),
+// inverse FFT_M;  post: y[o][k][i] = a[o][k][i] * c[k] / M (k < L).  Packed [outer][L or M][inner] layouts.
+template <typename T>
+__global__ void gen_blu_pre_kernel(const cplx<T> *__restrict__ x, cplx<T> *__restrict__ a, const double2 *__restrict__ chirp,
+                                   long long outer, int L, int M, long long inner) {
+    const long long total = outer * (long long)M * inner;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e % inner, r1 = e / inner;
+        const int j = (int)(r1 % M);
+        const long long o = r1 / M;
+        cplx<T> r;
+        r.x = r.y = (T)0;
+        if (j < L) {
+            const cplx<T> v = x[(o * L + j) * inner + i];
+            const double2 c = __ldg(chirp + j);
+            r.x = (T)((double)v.x * c.x - (double)v.y * c.y);
+            r.y = (T)((double)v.x * c.y + (double)v.y * c.x);
+        }
+        a[e] = r;
+    }
+}
+
+template <typename T>
+__global__ void gen_blu_mul_kernel(cplx<T> *__restrict__ a, const cplx<T> *__restrict__ bhat, long long outer, int M,
+                                   long long inner) {
+    const long long total = outer * (long long)M * inner;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)((e / inner) % M);
+        a[e] = cmul(a[e], __ldg(bhat + k));
+    }
+}
+
+template <typename T>
+__global__ void gen_blu_post_kernel(const cplx<T> *__restrict__ a, cplx<T> *__restrict__ y, const double2 *__restrict__ chirp,
+                                    long long outer, int L, int M, long long inner, double scale) {
+    const long long total = outer * (long long)L * inner;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e % inner, r1 = e / inner;
+        const int k = (int)(r1 % L);
+        const long long o = r1 / L;
+        const cplx<T> v = a[(o * M + k) * inner + i];
+        const double2 c = __ldg(chirp + k);
+        cplx<T> r;
+        r.x = (T)(((double)v.x * c.x - (double)v.y * c.y) * scale);
+        r.y = (T)(((double)v.x * c.y + (double)v.y * c.x) * scale);
+        y[e] = r;
+    }
+}
+
 // keep the first Lc of every L-long line: packed [lines][L] -> packed [lines][Lc]
 template <typename T>
 __global__ void gen_truncate_kernel(const cplx<T> *__restrict__ x, cplx<T> *__restrict__ y, long long lines, int L,

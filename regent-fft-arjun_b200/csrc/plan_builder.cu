@@ -213,26 +213,16 @@ bool add_tile_pass_with(Builder &B, const TileKernelInfo *ki, int variant, int L
     if (tiles * parts > 0x7fffffffll) return false;
     ln.grid = (unsigned)(tiles * parts);
     tp.n_tiles = (int)tiles;
-    {
-        // FFTB200_GRID_CAP=n (tuning): run single-CTA passes persistently on at most n CTAs
-        const int cap = env_int_or("FFTB200_GRID_CAP", 0);
-        if (cap > 0 && ki->cluster == 1 && variant == V_CC_PEER && ln.grid > (unsigned)cap) {
-            ln.grid = (unsigned)cap;
-            ln.ticket = (unsigned *)B.alloc(sizeof(unsigned));
-        }
-    }
-    tp.ticket = nullptr;
     tp.prefetch_tiles = 0;
     {
         // L2 prefetch of the tile that will run next in this CTA slot (distance = CTAs resident on the GPU).
         // Measured on B200 (512^3): strided-axis passes whose lines stay inside a few 2 MiB pages gain ~9 %
         // (fp64 y axis 0.760 -> 0.692 ms, 6.2 TB/s); passes with a multi-MiB line stride lose (z axis
         // 0.86 -> 1.12 ms) and contiguous-axis passes do not change, so only the first kind prefetches.
-        // FFTB200_PREFETCH=0 switches it off, =k forces distance k on every single-CTA pass (tuning).
-        const int forced = env_int_or("FFTB200_PREFETCH", -1);
+        // (1024^3 fp64, 128 KiB tiles: y axis 8.11 -> 7.23 ms with the prefetch.)
         const bool col_load = !load_row;
         const bool page_local = in_ls * (long long)(P->prec ? 16 : 8) <= 65536;
-        const int k = forced >= 0 ? forced : ((col_load && page_local) ? 1 : 0);
+        const int k = (col_load && page_local) ? 1 : 0;
         if (k > 0 && ki->cluster == 1) {
             int sms = 148, per_sm = 1;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P->device);
@@ -535,6 +525,111 @@ static unsigned grid_for(long long total) {
     return (unsigned)g;
 }
 
+static int largest_prime_factor(long long v) {
+    long long best = 1;
+    for (long long p = 2; p * p <= v; ++p)
+        while (v % p == 0) { best = p; v /= p; }
+    if (v > 1) best = v;
+    return (int)best;
+}
+
+// Prime factors above this run as Bluestein convolutions instead of O(L * p) radix-p stages (fftw-3.3.8/dft/bluestein.c,
+// dft/rader.c are the CPU path's answers to the same problem)
+static const int BLUESTEIN_MIN_PRIME = 31;
+
+// One axis of a generic plan by Bluestein's algorithm: packed [outer][L][inner] in buffer *cur -> the other work buffer.
+// The convolution runs through BUF_BLU ([outer][M][inner], M = 2^m >= 2L-1) with the library's own power-of-two tile
+// passes (forward, pointwise product with the transformed chirp, backward).  Returns false (nothing added) when M does
+// not fit a single tile pass; the caller then falls back to the radix-p stages.
+static bool add_bluestein_axis(Builder &B, int *cur, int axis, long long outer, int L, long long inner) {
+    Plan *P = B.P;
+    int M = 1;
+    while (M < 2 * L - 1) M *= 2;
+    const int variant = inner == 1 ? V_RR : V_CC;
+    if (!find_tile_kernel(P->prec, variant, M)) return false;
+    const size_t ce = P->prec ? 16 : 8;
+    const size_t need = (size_t)outer * M * inner * ce;
+    if (P->blu_bytes < need) {
+        void *nb = B.alloc(need);  // (earlier, smaller buffers stay owned by the plan; at most one per axis)
+        if (!nb) return false;
+        P->blu = nb;
+        P->blu_bytes = need;
+    }
+    // chirp c[j] = exp(-i pi j^2 / L) = w_{2L}^(j^2 mod 2L), exact integer reduction
+    std::vector<double> hc(2 * (size_t)L);
+    for (long long j = 0; j < L; ++j) twiddle((j * j) % (2ll * L), 2ll * L, &hc[2 * j], &hc[2 * j + 1]);
+    const double2 *chirp = (const double2 *)B.upload(hc.data(), hc.size() * sizeof(double));
+    if (!chirp) return false;
+    // b[j] = conj(c[j]) for |j| < L, wrapped into M points; Bhat = FFT_M(b), computed once on the device
+    void *bhat = nullptr;
+    {
+        std::vector<double> hb(2 * (size_t)M, 0.0);
+        for (long long j = 0; j < L; ++j) {
+            hb[2 * j] = hc[2 * j];
+            hb[2 * j + 1] = -hc[2 * j + 1];
+            if (j > 0) { hb[2 * (M - j)] = hc[2 * j]; hb[2 * (M - j) + 1] = -hc[2 * j + 1]; }
+        }
+        if (P->prec) {
+            bhat = B.upload(hb.data(), hb.size() * sizeof(double));
+        } else {
+            std::vector<float> hf(hb.begin(), hb.end());
+            bhat = B.upload(hf.data(), hf.size() * sizeof(float));
+        }
+        if (!bhat) return false;
+        Plan *sub = nullptr;
+        const long long nn[1] = {M}, st[2] = {M, 1};
+        if (create_plan(&sub, 1, nn, 1, st, st, P->prec ? FFTB200_Z2Z : FFTB200_C2C, false) != FFTB200_SUCCESS) return false;
+        const int rc = exec_plan(sub, bhat, bhat, FFTB200_FORWARD);
+        cudaStreamSynchronize(sub->stream);
+        delete sub;
+        if (rc != FFTB200_SUCCESS) return false;
+    }
+    const long long total_m = outer * M * inner, total_l = outer * L * inner;
+    auto grid = [](long long t) { long long g = (t + 255) / 256; if (g > 148ll * 64) g = 148ll * 64; return (unsigned)(g < 1 ? 1 : g); };
+    char buf[200];
+    Launch pre;
+    pre.kind = Launch::BLU_PRE;
+    pre.outer = outer; pre.inner = inner; pre.L = L; pre.M = M; pre.chirp = chirp;
+    pre.src = *cur; pre.dst = BUF_BLU;
+    pre.total = total_m; pre.grid = grid(total_m);
+    pre.algo_bytes = (unsigned long long)(total_l + total_m) * ce;
+    snprintf(buf, sizeof buf, "bluestein axis=%d L=%d M=%d: chirp multiply + zero pad, lines=%lld", axis, L, M, outer * inner);
+    pre.desc = buf;
+    P->launches.push_back(pre);
+    for (int dir = 1; dir <= 2; ++dir) {
+        std::vector<Level> lv;
+        if (inner == 1) lv = {{outer, (long long)M, (long long)M}};
+        else lv = {{inner, 1, 1}, {outer, M * inner, M * inner}};
+        if (!add_tile_pass(B, variant, M, inner, inner, lv, BUF_BLU, BUF_BLU, 0,
+                           dir == 1 ? "bluestein convolution: forward FFT" : "bluestein convolution: backward FFT"))
+            return false;
+        P->launches.back().dir_override = dir;
+        if (dir == 1) {
+            Launch mul;
+            mul.kind = Launch::BLU_MUL;
+            mul.outer = outer; mul.inner = inner; mul.M = M; mul.bhat = bhat;
+            mul.src = BUF_BLU; mul.dst = BUF_BLU;
+            mul.total = total_m; mul.grid = grid(total_m);
+            mul.algo_bytes = (unsigned long long)total_m * ce * 2ull;
+            snprintf(buf, sizeof buf, "bluestein axis=%d M=%d: product with the transformed chirp", axis, M);
+            mul.desc = buf;
+            P->launches.push_back(mul);
+        }
+    }
+    Launch post;
+    post.kind = Launch::BLU_POST;
+    post.outer = outer; post.inner = inner; post.L = L; post.M = M; post.chirp = chirp;
+    post.src = BUF_BLU;
+    post.dst = (*cur == BUF_WORK0) ? BUF_WORK1 : BUF_WORK0;
+    post.total = total_l; post.grid = grid(total_l);
+    post.algo_bytes = (unsigned long long)(total_l + total_m) * ce;
+    snprintf(buf, sizeof buf, "bluestein axis=%d L=%d M=%d: chirp multiply, scale 1/M, truncate", axis, L, M);
+    post.desc = buf;
+    P->launches.push_back(post);
+    *cur = post.dst;
+    return B.err == FFTB200_SUCCESS;
+}
+
 static bool build_generic(Builder &B) {
     Plan *P = B.P;
     const int rank = P->rank;
@@ -572,7 +667,9 @@ static bool build_generic(Builder &B) {
         long long outer = P->batch, inner = 1;
         for (int d = 0; d < axis; ++d) outer *= dims[d];
         for (int d = axis + 1; d < rank; ++d) inner *= dims[d];
-        if (L > 1) {
+        if (L > 1 && largest_prime_factor(L) > BLUESTEIN_MIN_PRIME && add_bluestein_axis(B, &cur, axis, outer, L, inner)) {
+            // (length with a large prime factor: chirp-z through a power-of-two convolution, O(L log L) per line)
+        } else if (L > 1) {
             const double2 *tw = (const double2 *)B.table(L, L, true);
             int rem = L, Ns = 1;
             for (int p = 2; rem > 1; ++p) {

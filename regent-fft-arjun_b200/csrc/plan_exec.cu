@@ -10,10 +10,6 @@ namespace fftb200 {
 
 // one launch of a tile pass; cluster kernels go through cudaLaunchKernelEx with the cluster dimension
 cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st, const TileParams &tp) {
-    if (tp.ticket) {
-        const cudaError_t e = cudaMemsetAsync(tp.ticket, 0, sizeof(unsigned), st);
-        if (e != cudaSuccess) return e;
-    }
     if (ki->cluster <= 1) {
         ki->fn<<<grid, ki->threads, ki->smem_bytes, st>>>(tp);
         return cudaGetLastError();
@@ -117,6 +113,16 @@ template <typename T> static cudaError_t launch_generic(const Launch &ln, const 
         case Launch::GEN_SCATTER:
             gen_scatter_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.lay, ln.total, inverse);
             break;
+        case Launch::BLU_PRE:
+            gen_blu_pre_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.chirp, ln.outer, ln.L, ln.M, ln.inner);
+            break;
+        case Launch::BLU_MUL:
+            gen_blu_mul_kernel<T><<<ln.grid, 256, 0, st>>>((C *)dst, (const C *)ln.bhat, ln.outer, ln.M, ln.inner);
+            break;
+        case Launch::BLU_POST:
+            gen_blu_post_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.chirp, ln.outer, ln.L, ln.M, ln.inner,
+                                                            1.0 / (double)ln.M);
+            break;
         default: break;
     }
     return cudaGetLastError();
@@ -151,8 +157,8 @@ static int run_launches(Plan *P, const void *in, void *out, int inverse) {
     }
     for (size_t i = 0; i < nl; ++i) {
         const Launch &ln = P->launches[i];
-        const void *bufs_src[4] = {in, out, P->work[0], P->work[1]};
-        void *bufs_dst[4] = {nullptr, out, P->work[0], P->work[1]};
+        const void *bufs_src[5] = {in, out, P->work[0], P->work[1], P->blu};
+        void *bufs_dst[5] = {nullptr, out, P->work[0], P->work[1], P->blu};
         const void *src = bufs_src[ln.src];
         void *dst = bufs_dst[ln.dst];
         cudaError_t ce;
@@ -161,8 +167,7 @@ static int run_launches(Plan *P, const void *in, void *out, int inverse) {
             const size_t elt = P->prec ? 16 : 8;  // launch offsets are in complex elements
             tp.in = (const char *)src + (size_t)ln.in_off * elt;
             tp.out = (char *)dst + (size_t)ln.out_off * elt;
-            tp.inverse = inverse;
-            tp.ticket = ln.ticket;
+            tp.inverse = ln.dir_override ? (ln.dir_override == 2) : inverse;
             ce = launch_tile(ln.ki, ln.grid, P->stream, tp);
         } else {
             ce = P->prec ? launch_generic<double>(ln, src, dst, inverse, P->stream)

@@ -16,10 +16,10 @@
 
 namespace fftb200 {
 
-enum BufSel { BUF_IN = 0, BUF_OUT = 1, BUF_WORK0 = 2, BUF_WORK1 = 3 };
+enum BufSel { BUF_IN = 0, BUF_OUT = 1, BUF_WORK0 = 2, BUF_WORK1 = 3, BUF_BLU = 4 };
 
 struct Launch {
-    enum Kind { TILE, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER } kind = TILE;
+    enum Kind { TILE, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER, BLU_PRE, BLU_MUL, BLU_POST } kind = TILE;
     // TILE
     const TileKernelInfo *ki = nullptr;
     TileParams tp{};
@@ -30,9 +30,14 @@ struct Launch {
     int L = 0, p = 0, Ns = 0, Lc = 0;
     const double2 *gtw = nullptr;
     bool real_in = false;
+    // Bluestein (generic path): padded length, chirp table, transformed kernel; tile passes inside a generic plan run
+    // in a fixed direction whatever the plan's (dir_override: 0 = the plan's direction, 1 = forward, 2 = backward)
+    int M = 0;
+    const double2 *chirp = nullptr;
+    const void *bhat = nullptr;
+    int dir_override = 0;
     // common
     long long in_off = 0, out_off = 0;  // element offsets added to the source / destination base (chunked passes)
-    unsigned *ticket = nullptr;         // persistent (capped) launches: dynamic tile counter, zeroed before every launch
     int src = BUF_IN, dst = BUF_OUT;
     unsigned grid = 0;
     unsigned long long algo_bytes = 0;
@@ -54,6 +59,8 @@ struct Plan {
     std::vector<Launch> launches;
     std::vector<void *> dev_allocs;
     void *work[2] = {nullptr, nullptr};
+    void *blu = nullptr;  // Bluestein convolution buffer (generic plans with a large prime factor)
+    size_t blu_bytes = 0;
     size_t work_bytes = 0;
     bool profiling = false;
     // profiling: one row of (launches + 1) events per recorded exec, up to PROF_MAX_EXECS rows

@@ -4,16 +4,17 @@
 //
 // Round 1 ran this as 2 + 2 * chunks tile launches plus 2 + 2 * chunks one-warp signal / wait kernels on two streams
 // chained by events; at 8 GPUs x 512^3 those hand-shake launches and stream hops were 0.10-0.17 ms of a 0.59 ms step.
-// Here the CTAs of ONE launch draw tickets from a counter; the ticket order is
-//     Y(0) Y(1) | X(0) Y(2) | X(1) Y(3) | ... | X(J-2) | X(J-1) | Z
-// (Y(c) = y-axis tiles of plane chunk c, X(c) = x-axis tiles of the rows of the receive slab whose plane lies in chunk c
-// of any rank, Z = z-axis tiles), so that
+// Here the CTAs of ONE launch draw tickets from two queues,
+//     exchange queue:  Y(0) Y(1) ... Y(J-1)          (Y(c) = y-axis tiles of plane chunk c; NVLink-bound)
+//     local queue:     X(0) X(1) ... X(J-1) Z        (X(c) = x-axis tiles of the rows of the receive slab whose plane lies
+//                                                      in chunk c of any rank; Z = z-axis tiles; HBM-bound)
+// half of them serving the exchange queue first, the other half the local queue, and
 //   * the last tile of Y(c) to finish publishes "chunk c written" to every peer (system-scope release store),
 //   * an X(c) tile first waits (one thread, system-scope acquire loads) until every peer has published chunk c,
 //   * a Z tile first waits until every X tile of this rank has been stored.
-// A waiting CTA keeps its SM slot but never blocks the tickets before it: Y tiles wait for nothing but the peers'
-// "receive slab free" flags of this epoch, which every rank publishes when its kernel starts.  No cooperative launch is
-// needed: tickets are handed out in order, so whatever a ticket waits for is already running or finished somewhere.
+// A waiting CTA keeps its SM slot but cannot block what it waits for: Y tiles wait for nothing but the peers' "receive
+// slab free" flags of this epoch, which every rank publishes when its kernel starts, and each queue is handed out in
+// order.  No cooperative launch is needed.
 //
 // No reference counterpart (src/fft.rg has no distributed transform); the decomposition is FFTW-MPI's
 // (fftw-3.3.8/mpi/dft-rank-geq2.c:40-59, mpi/transpose-alltoall.c:49-100, doc/mpi.texi:443-466), see slab_plan.cu.
@@ -24,7 +25,8 @@ namespace fftb200 {
 
 struct SlabFusedParams {
     TileParams y, x, z;       // whole passes: y over all local planes, x over one chunk's rows (+ chunk shift), z over all
-    unsigned *counters;        // [0] ticket, [1] finished x tiles, [2 + c] finished y tiles of chunk c; zeroed before launch
+    unsigned *counters;        // [0] exchange-queue ticket, [1] local-queue ticket, [2] finished x tiles,
+                               // [3 + c] finished y tiles of chunk c; zeroed before every launch
     unsigned long long *flags[MAX_PEERS];  // every rank's flag block (mine included): [kind][source rank] epochs
     int *err;                  // mapped host word: a wait that gave up records it here
     unsigned long long epoch;
@@ -78,101 +80,109 @@ fft_slab_fused_kernel(const SlabFusedParams p) {
     using TZ = TileTraits<T, L, R, W, V_CC>;
     static_assert(TY::THREADS == TX::THREADS && TX::THREADS == TZ::THREADS, "the three passes share one CTA shape");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_ticket[2];
+    __shared__ int s_ticket;
     const int J = p.n_chunks;
-    // ticket layout: group g in [0, J+1]: X(g-2)... see the header.  Slot s = 0..J+1 holds Y(s) (if s < J) after X(s-2) (if s >= 2)
     const int per_y = p.tiles_y_chunk, per_x = p.tiles_x_chunk;
-    const int total = J * (per_y + per_x) + p.tiles_z;
+    const int total_ex = J * per_y;                 // exchange queue: Y(0) .. Y(J-1)
+    const int total_loc = J * per_x + p.tiles_z;    // local queue:    X(0) .. X(J-1), Z
+    unsigned *ex_ticket = p.counters, *loc_ticket = p.counters + 1, *x_done = p.counters + 2, *y_done = p.counters + 3;
 
     // this rank's receive slab is free again (stream order: its previous transform's z pass has finished)
     if (blockIdx.x == 0 && (int)threadIdx.x < p.G)
         fused_st_release_sys(p.flags[threadIdx.x] + (size_t)0 * MAX_PEERS + p.me, p.epoch);
 
-    bool peers_free = false;
-    int cur = 0;
-    if (threadIdx.x == 0) s_ticket[0] = (int)atomicAdd(p.counters, 1u);
-    __syncthreads();
-    for (;;) {
-        const int ticket = s_ticket[cur];
-        if (ticket >= total) break;
-        unsigned next_ticket = 0;
-        if (threadIdx.x == 0) next_ticket = atomicAdd(p.counters, 1u);  // its latency hides behind this tile
-        // decode: slots s = 0 .. J+1; slot s holds X(s-2) first (s >= 2), then Y(s) (s < J); then all of Z
-        int phase, chunk, t;  // phase 0 = Y, 1 = X, 2 = Z
-        {
-            int r = ticket;
-            const int head = 2 * per_y;                       // slots 0 and 1: Y(0), Y(1) only (fewer if J < 2)
-            const int n_head = J < 2 ? J : 2;
-            if (r < n_head * per_y) {
-                phase = 0; chunk = r / per_y; t = r - chunk * per_y;
-            } else {
-                r -= n_head * per_y;
-                const int mid_slots = J > 2 ? J - 2 : 0;      // slots 2 .. J-1: X(s-2) then Y(s)
-                const int per_slot = per_x + per_y;
-                if (r < mid_slots * per_slot) {
-                    const int s = r / per_slot, q = r - s * per_slot;
-                    if (q < per_x) { phase = 1; chunk = s; t = q; }
-                    else { phase = 0; chunk = s + 2; t = q - per_x; }
-                } else {
-                    r -= mid_slots * per_slot;
-                    const int tail_x = (J < 2 ? J : 2) * per_x;  // X(J-2), X(J-1)  (X(0) only if J == 1)
-                    if (r < tail_x) {
-                        const int k = r / per_x;
-                        phase = 1; chunk = (J < 2 ? 0 : J - 2) + k; t = r - k * per_x;
-                    } else {
-                        phase = 2; chunk = 0; t = r - tail_x;
-                    }
+    // Two queues, two roles.  The exchange pass is NVLink-bound and its CTAs sit in store back-pressure; the x / z passes
+    // are HBM-bound.  Half the CTAs (the first half of the grid: one per SM when two fit) serve the exchange queue first,
+    // the others the local queue, so both links stay busy; a CTA whose own queue is empty helps with the other one.
+    //
+    // Completion is published per CTA and per chunk, not per tile: a system-scope fence after peer stores costs a full
+    // NVLink round trip, and one per tile serialised every CTA (measured: 2 x B200, 512^3: 1.88 ms against 1.36 ms for
+    // the multi-launch path).  A CTA counts the tiles it finished in the current (kind, chunk) and adds them to the
+    // chunk's counter - one fence, one atomic - when its next ticket belongs to something else or its queue runs dry;
+    // always before it waits for anything.
+    const bool ex_role = blockIdx.x < (gridDim.x + 1) / 2;
+    bool ex_open = true, loc_open = true, peers_free = false, x_all_done = false;
+    unsigned ready_mask = 0;                       // chunks whose arrival this CTA has already observed
+    int pend_kind = 0, pend_chunk = 0;             // 1 = Y tiles, 2 = X tiles finished but not yet published
+    unsigned pend_count = 0;
+    auto flush = [&]() {
+        if (pend_kind != 0 && threadIdx.x == 0) {
+            if (pend_kind == 1) {
+                __threadfence_system();
+                const unsigned done = atomicAdd(y_done + pend_chunk, pend_count);
+                if (done + pend_count == (unsigned)per_y) {
+                    __threadfence_system();
+                    for (int d = 0; d < p.G; ++d)
+                        fused_st_release_sys(p.flags[d] + (size_t)(1 + pend_chunk) * MAX_PEERS + p.me, p.epoch);
                 }
+            } else {
+                __threadfence();
+                atomicAdd(x_done, pend_count);
             }
-            (void)head;
         }
-        if (phase == 0) {
+        pend_kind = 0;
+        pend_count = 0;
+    };
+    while (ex_open || loc_open) {
+        const bool take_ex = ex_open && (ex_role || !loc_open);
+        if (threadIdx.x == 0) s_ticket = (int)atomicAdd(take_ex ? ex_ticket : loc_ticket, 1u);
+        __syncthreads();
+        const int ticket = s_ticket;
+        __syncthreads();  // s_ticket may be rewritten
+        if (take_ex) {
+            if (ticket >= total_ex) { ex_open = false; flush(); continue; }
+            const int chunk = ticket / per_y;
+            if (pend_kind != 0 && (pend_kind != 1 || pend_chunk != chunk)) flush();
             if (!peers_free) {
                 // the first store into a peer's receive slab waits until that peer has released it for this epoch
                 if (threadIdx.x == 0 && p.G > 1) fused_wait_peers(p, 0);
                 __syncthreads();
                 peers_free = true;
             }
-            fft_tile_body<T, L, R, W, V_CC_PEER>(p.y, chunk * per_y + t, smem_raw);
-            __syncthreads();  // every thread's peer stores are issued
-            if (threadIdx.x == 0) {
-                __threadfence_system();
-                const unsigned done = atomicAdd(p.counters + 2 + chunk, 1u);
-                if (done == (unsigned)per_y - 1) {
-                    __threadfence_system();
-                    for (int d = 0; d < p.G; ++d) fused_st_release_sys(p.flags[d] + (size_t)(1 + chunk) * MAX_PEERS + p.me, p.epoch);
-                }
-            }
-        } else if (phase == 1) {
-            if (threadIdx.x == 0) fused_wait_peers(p, 1 + chunk);  // (G == 1: my own flag, published by my last Y tile)
-            __syncthreads();
-            const long long sh = (long long)chunk * p.x_chunk_shift;
-            fft_tile_body<T, L, R, W, V_RR, true>(p.x, t, smem_raw, sh, sh);
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence();
-                atomicAdd(p.counters + 1, 1u);
-            }
+            fft_tile_body<T, L, R, W, V_CC_PEER>(p.y, ticket, smem_raw);
+            pend_kind = 1;
+            pend_chunk = chunk;
+            ++pend_count;
         } else {
-            if (threadIdx.x == 0) {
-                const unsigned want = (unsigned)(J * per_x);
-                const unsigned long long t0 = fused_global_ns();
-                unsigned spins = 0;
-                while (fused_ld_acquire_gpu(p.counters + 1) < want) {
-                    __nanosleep(100);
-                    if ((++spins & 0x3ff) == 0 && fused_global_ns() - t0 > FUSED_WAIT_TIMEOUT_NS) {
-                        *reinterpret_cast<volatile int *>(p.err) = 99;
-                        break;
-                    }
+            if (ticket >= total_loc) { loc_open = false; flush(); continue; }
+            if (ticket < J * per_x) {
+                const int chunk = ticket / per_x, t = ticket - chunk * per_x;
+                if (pend_kind != 0 && pend_kind != 2) flush();
+                if (!((ready_mask >> chunk) & 1u)) {
+                    flush();  // never wait with unpublished work
+                    if (threadIdx.x == 0) fused_wait_peers(p, 1 + chunk);  // (G == 1: my own flag, set by my last Y tile)
+                    __syncthreads();
+                    ready_mask |= 1u << chunk;
                 }
+                const long long sh = (long long)chunk * p.x_chunk_shift;
+                fft_tile_body<T, L, R, W, V_RR, true>(p.x, t, smem_raw, sh, sh);
+                pend_kind = 2;
+                pend_chunk = 0;
+                ++pend_count;
+            } else {
+                flush();
+                if (!x_all_done) {
+                    if (threadIdx.x == 0) {
+                        const unsigned want = (unsigned)(J * per_x);
+                        const unsigned long long t0 = fused_global_ns();
+                        unsigned spins = 0;
+                        while (fused_ld_acquire_gpu(x_done) < want) {
+                            __nanosleep(100);
+                            if ((++spins & 0x3ff) == 0 && fused_global_ns() - t0 > FUSED_WAIT_TIMEOUT_NS) {
+                                *reinterpret_cast<volatile int *>(p.err) = 99;
+                                break;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    x_all_done = true;
+                }
+                fft_tile_body<T, L, R, W, V_CC, true>(p.z, ticket - J * per_x, smem_raw);
             }
-            __syncthreads();
-            fft_tile_body<T, L, R, W, V_CC, true>(p.z, t, smem_raw);
         }
-        if (threadIdx.x == 0) s_ticket[cur ^ 1] = (int)next_ticket;
-        __syncthreads();  // next ticket visible; this tile's shared memory free
-        cur ^= 1;
+        __syncthreads();  // this tile's stores are issued by every thread; its shared memory is free
     }
+    flush();
 }
 
 struct SlabFusedKernelInfo {

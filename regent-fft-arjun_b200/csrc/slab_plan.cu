@@ -155,7 +155,6 @@ static int slab_launch(Plan *P, int idx, const void *src, void *dst, void *const
     tp.in = (const char *)src + (size_t)ln.in_off * ce;
     tp.out = dst ? (char *)dst + (size_t)ln.out_off * ce : nullptr;
     tp.inverse = inverse;
-    tp.ticket = ln.ticket;
     if (peers)
         for (int d = 0; d < npeers; ++d) tp.peer[d] = (char *)peers[d] + (size_t)ln.out_off * ce;
     return launch_tile(ln.ki, ln.grid, st, tp) == cudaSuccess ? FFTB200_SUCCESS : FFTB200_EXEC_FAILED;
@@ -254,7 +253,7 @@ int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, in
         // The exchange pass is NVLink-bound, not SM-bound: when it is pipelined against the z-axis pass
         // keep it persistent on a bounded number of CTAs so that the HBM-bound pass finds free SMs.
         if (G > 1 && S->J > 1) {
-            const unsigned cap = (unsigned)env_int_or("FFTB200_SLAB_P2_CTAS", 148);
+            const unsigned cap = 148u;
             // static tile assignment on purpose: with dynamic tickets (TileParams::ticket) every capped CTA stays
             // resident until the chunk ends and the overlapped pass starves (2 x B200, 512^3: 1.61 vs 1.40 ms)
             if (cap > 0 && ln.grid > cap) ln.grid = std::max(1u, cap / ln.ki->cluster) * ln.ki->cluster;
@@ -312,7 +311,7 @@ int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, in
             ln.out_off = ((long long)rank * S->n0l + (long long)c * pc) * S->n2p;
             set_peer(ln);
             if (G > 1 && S->Jp > 1 && ln.ki->cluster == 1) {  // (a capped cluster pass pays a cluster barrier per tile)
-                const unsigned cap = (unsigned)env_int_or("FFTB200_SLAB_P2_CTAS", 148);
+                const unsigned cap = 148u;
                 if (cap > 0 && ln.grid > cap) ln.grid = cap;  // static assignment, see the R2C pipeline above
             }
             S->l_y.push_back((int)P->launches.size() - 1);
@@ -336,7 +335,13 @@ int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, in
         // ---- the same three passes for the fused single-kernel path (cubes whose side has a fused kernel):
         // y over ALL local planes, x over one chunk's rows (the kernel adds the chunk shift), z over everything
         const SlabFusedKernelInfo *fk = (S->n0 == S->n1 && S->n1 == S->n2) ? find_slab_fused_kernel(P->prec, (int)S->n0) : nullptr;
-        if (fk && env_int_or("FFTB200_SLAB_FUSED", 1) != 0 && pc >= fk->W && S->n2p == S->n2) {
+        // Default: only where two of its CTAs fit an SM (tiles of at most 64 KiB), so that an exchange-queue CTA and a
+        // local-queue CTA share every SM.  With 128 KiB tiles (1024^3) each role gets half the SMs to itself and the
+        // multi-launch path, whose 64 KiB x-axis tiles co-reside with the exchange pass, is faster (2 x B200, 1024^3:
+        // 12.3 ms against 17.2 ms); FFTB200_SLAB_FUSED=1 / 0 force the choice.
+        const int fused_mode = env_int_or("FFTB200_SLAB_FUSED", -1);
+        const bool fused_on = fk && (fused_mode == 1 || (fused_mode != 0 && fk->smem_bytes <= 64 * 1024));
+        if (fused_on && pc >= fk->W && S->n2p == S->n2) {
             S->fused_ki = TileKernelInfo{reinterpret_cast<void (*)(const TileParams)>(fk->fn), fk->L, fk->R, fk->W, fk->threads,
                                          fk->smem_bytes, 1};
             bool ok = true;
@@ -365,7 +370,7 @@ int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, in
                 if (ok) S->l_fz = (int)P->launches.size() - 1;
             }
             if (ok) {
-                S->fused_counters = (unsigned *)B.alloc(sizeof(unsigned) * (size_t)(2 + S->Jp));
+                S->fused_counters = (unsigned *)B.alloc(sizeof(unsigned) * (size_t)(3 + S->Jp));
                 int sms = 148, per_sm = 1;
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P->device);
                 if (fk->smem_bytes > 48 * 1024)
@@ -518,7 +523,7 @@ static int slab_exec_p2p_body(Plan *P, const void *in, void *out, int inverse, c
         fp.tiles_y_chunk = ly.tp.n_tiles / S->Jp;
         fp.tiles_x_chunk = lx.tp.n_tiles;
         fp.tiles_z = lz.tp.n_tiles;
-        if (cudaMemsetAsync(S->fused_counters, 0, sizeof(unsigned) * (size_t)(2 + S->Jp), st) != cudaSuccess) return FFTB200_EXEC_FAILED;
+        if (cudaMemsetAsync(S->fused_counters, 0, sizeof(unsigned) * (size_t)(3 + S->Jp), st) != cudaSuccess) return FFTB200_EXEC_FAILED;
         if (S->timing) cudaEventRecord(S->ev_t[1], st);
         S->fused->fn<<<S->fused_grid, S->fused->threads, S->fused->smem_bytes, st>>>(fp);
         if (S->timing) { cudaEventRecord(S->ev_t[2], st); cudaEventRecord(S->ev_t[3], st); }

@@ -61,7 +61,6 @@ struct TileParams {
     long long in_ls, in_is, in_os1, in_os2;
     long long out_ls, out_is, out_os1, out_os2;
     int n_tiles;   // tiles of the whole pass (a CTA loops over tile = blockIdx.x + k * gridDim.x)
-    unsigned *ticket;    // != nullptr: persistent launch, tiles handed out by atomicAdd (zeroed before the launch)
     int prefetch_tiles;  // > 0: every CTA asks L2 to prefetch the input of tile + prefetch_tiles (the tile the
                          // CTA slot it occupies will run next), decoupling HBM latency from SM occupancy
     int n_inner;   // lines along the inner index
@@ -535,31 +534,14 @@ fft_tile_kernel(const TileParams p) {
     // registers at the 64-register cap (measured: ~4 % on the 512^3 strided passes).
     if constexpr (VAR != V_CC_PEER) {
         fft_tile_body<T, L, R, W, VAR>(p, (int)blockIdx.x, smem_raw);
-        return;
-    }
-    if (p.ticket != nullptr) {
-        // persistent launch with DYNAMIC tile assignment: SMs do not run at the same speed (two dies, near and far
-        // L2), so a static tile = blockIdx.x + k*gridDim.x split leaves the whole pass waiting for the slowest
-        // CTA (measured: 512^3 y axis 0.70 ms with one CTA per tile, 1.03 ms on 296 static persistent CTAs)
-        __shared__ int s_tile[2];
-        int cur = 0;
-        if (threadIdx.x == 0) s_tile[0] = (int)atomicAdd(p.ticket, 1u);
-        __syncthreads();
-        for (;;) {
-            const int tile = s_tile[cur];
-            if (tile >= p.n_tiles) break;
-            unsigned next = 0;
-            if (threadIdx.x == 0) next = atomicAdd(p.ticket, 1u);  // consumed after the tile: latency hidden
+    } else {
+        // static tile = blockIdx.x + k * gridDim.x assignment on purpose: a capped exchange pass should drain early on
+        // the fast SMs so that the pass it overlaps with finds them free (dynamic tickets kept every capped CTA resident
+        // to the end: 2 x B200, 512^3: 1.61 vs 1.40 ms)
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             fft_tile_body<T, L, R, W, VAR>(p, tile, smem_raw);
-            if (threadIdx.x == 0) s_tile[cur ^ 1] = (int)next;
-            __syncthreads();
-            cur ^= 1;
+            if (TileTraits<T, L, R, W, VAR>::NEED_SMEM && tile + (int)gridDim.x < p.n_tiles) __syncthreads();
         }
-        return;
-    }
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        fft_tile_body<T, L, R, W, VAR>(p, tile, smem_raw);
-        if (TileTraits<T, L, R, W, VAR>::NEED_SMEM && tile + (int)gridDim.x < p.n_tiles) __syncthreads();
     }
 }
 

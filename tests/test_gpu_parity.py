@@ -806,6 +806,29 @@ def test_inverse_real_transforms(L, oracle):
     assert lib.fftb200_plan_many(ctypes.byref(hbad), 1, n3, None, 0, 0, None, 0, 0, L.Z2D, 1) == L.UNSUPPORTED   # not 2^k
 
 
+def test_large_prime_lengths_use_bluestein(L, oracle):
+    """Lengths with a prime factor above 31 run as Bluestein convolutions through the power-of-two tile passes
+    (fftw-3.3.8/dft/bluestein.c is the CPU path's counterpart) instead of O(L * p) radix-p stages; small primes
+    (the reference's own 3, 5, {3,3,2}: test/fft_test.rg:143,247,328,349) keep the radix stages."""
+    for kind, shape in [("z2z", (1021,)), ("z2z", (2039,)), ("z2z", (4099,)), ("c2c", (8191,)), ("d2z", (1021,)),
+                        ("z2z", (4, 521)), ("z2z", (97, 6)), ("z2z", (5, 67, 3)), ("r2c", (3, 1009)), ("z2z", (2 * 127, 4))]:
+        _, dt_in, _ = _kinds(L)[kind]
+        x = oracle.synth(shape, dt_in, 990 + len(shape))
+        got, desc = gpu_fft(L, kind, x, shape)
+        assert "bluestein" in desc, desc
+        err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape))
+        assert err <= oracle.tolerance(int(np.prod(shape)), kind in ("c2c", "r2c")), (kind, shape, err)
+        if kind in ("z2z", "c2c"):
+            back, _ = gpu_fft(L, kind, got, shape, direction=+1)
+            assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * oracle.tolerance(int(np.prod(shape)), kind == "c2c")
+    for kind, shape in [("z2z", (3, 3, 2)), ("z2z", (5,)), ("z2z", (1000,)), ("z2z", (31 * 4,))]:
+        _, dt_in, _ = _kinds(L)[kind]
+        x = oracle.synth(shape, dt_in, 995)
+        got, desc = gpu_fft(L, kind, x, shape)
+        assert "bluestein" not in desc and "generic stage" in desc, desc
+        assert oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape)) <= oracle.tolerance(int(np.prod(shape)), False)
+
+
 def test_inplace_r2c_padded_layout(L, oracle):
     """In-place R2C / D2Z with FFTW's padded format (rows of 2*(n/2+1) reals; fftw-3.3.8/doc/reference.texi, "Real-data
     DFT Array Format"): the half spectrum overwrites the real rows it came from.  1-D, 2-D, 3-D (the 3-D case also takes

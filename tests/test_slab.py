@@ -147,7 +147,7 @@ def test_slab_single_kernel_cubes_single_rank(fft, oracle, kind, side, planes, m
     for fused in ("1", "0"):
         monkeypatch.setenv("FFTB200_SLAB_FUSED", fused)
         plan = D.SlabFFT3D(shape, dt, rank=0, world=1, device="cuda:0", mode="p2p")
-        assert (fft._lib.launch_count(plan.engine.h) == 1) == (fused == "1")
+        assert (fft._lib.launch_count(plan.engine.h) == 1) == (fused == "1"), fft._lib.describe(plan.engine.h)
         for _ in range(3):
             plan.execute(xd)
         torch.cuda.synchronize()

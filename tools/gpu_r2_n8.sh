@@ -1,0 +1,13 @@
+#!/bin/bash
+# eight GPUs: the bench line as the driver runs it, plus slab probes (fused single kernel vs multi-launch, 1024^3 C2C and R2C)
+mkdir -p gpurun_out
+N=${1:-8}
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29631 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_bench_n${N}.json 2> gpurun_out/r02_bench_n${N}.err; echo "bench rc=$?"
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/r02_bench_n${N}.json").read().strip().split("\n")[-1])
+print("N=$N 512^3 ms", round(d["ms_per_step"],4), "GF", round(d["value"]), "launches/step", d["gpu_launches"]/d["steps"], "parity", d["parity"], "\n 1024^3", {k:d["scaling_1024"].get(k) for k in ("ms","GFLOP/s","parity")}, "\n e2e", {k:d["e2e"].get(k) for k in ("value","ms_per_step","host_link_GB/s_each_way","host_placement")})
+PY
+tail -n 3 gpurun_out/r02_bench_n${N}.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29632 tools/slab_probe2.py z2z:512:FFTB200_SLAB_FUSED=1 z2z:512:FFTB200_SLAB_FUSED=0 z2z:512:FFTB200_SLAB_FUSED=1,FFTB200_SLAB_PLANE_CHUNKS=2 z2z:512:FFTB200_SLAB_FUSED=1,FFTB200_SLAB_PLANE_CHUNKS=8 z2z:1024:FFTB200_SLAB_FUSED=0 z2z:1024:FFTB200_SLAB_FUSED=1 z2z:1024:FFTB200_SLAB_FUSED=0,FFTB200_SLAB_PLANE_CHUNKS=8 d2z:1024 c2c:512 > gpurun_out/r02_slab_probe_n${N}.jsonl 2> gpurun_out/r02_slab_probe_n${N}.err; echo "probe rc=$?"
+cat gpurun_out/r02_slab_probe_n${N}.jsonl; tail -n 3 gpurun_out/r02_slab_probe_n${N}.err
