@@ -294,8 +294,14 @@ int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, in
     // lies in chunk c of any rank) start as soon as chunk c has arrived from every rank: it hides under the
     // NVLink transfer of the following chunks, and only the z-axis pass is left after the exchange.
     if (!P->real) {
+        // (decided here because the chunk count depends on it; see the fused block below)
+        const SlabFusedKernelInfo *fk = (S->n0 == S->n1 && S->n1 == S->n2) ? find_slab_fused_kernel(P->prec, (int)S->n0) : nullptr;
+        const int fused_mode = env_int_or("FFTB200_SLAB_FUSED", -1);
+        const bool fused_on = fk && S->n2p == S->n2 && (fused_mode == 1 || (fused_mode != 0 && fk->smem_bytes <= 64 * 1024));
         int want = env_int_or("FFTB200_SLAB_PLANE_CHUNKS", 0);
-        if (want <= 0) want = (G > 1) ? 4 : 1;
+        // automatic: 4 plane chunks; the single-kernel path keeps chunks of at least 32 planes (8 x B200, 512^3:
+        // 2 chunks of 32 planes 0.583 ms, 4 of 16 0.615 ms; 4 x B200: 4 chunks of 32 planes 0.925 ms, 2 of 64 0.954 ms)
+        if (want <= 0) want = (G > 1) ? (fused_on ? (int)std::max<long long>(1, std::min<long long>(4, S->n0l / 32)) : 4) : 1;
         long long Jp = 1;
         while (Jp * 2 <= want && S->n0l % (Jp * 2) == 0) Jp *= 2;
         S->Jp = (int)Jp;
@@ -334,14 +340,11 @@ int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, in
         }
         // ---- the same three passes for the fused single-kernel path (cubes whose side has a fused kernel):
         // y over ALL local planes, x over one chunk's rows (the kernel adds the chunk shift), z over everything
-        const SlabFusedKernelInfo *fk = (S->n0 == S->n1 && S->n1 == S->n2) ? find_slab_fused_kernel(P->prec, (int)S->n0) : nullptr;
         // Default: only where two of its CTAs fit an SM (tiles of at most 64 KiB), so that an exchange-queue CTA and a
         // local-queue CTA share every SM.  With 128 KiB tiles (1024^3) each role gets half the SMs to itself and the
         // multi-launch path, whose 64 KiB x-axis tiles co-reside with the exchange pass, is faster (2 x B200, 1024^3:
         // 12.3 ms against 17.2 ms); FFTB200_SLAB_FUSED=1 / 0 force the choice.
-        const int fused_mode = env_int_or("FFTB200_SLAB_FUSED", -1);
-        const bool fused_on = fk && (fused_mode == 1 || (fused_mode != 0 && fk->smem_bytes <= 64 * 1024));
-        if (fused_on && pc >= fk->W && S->n2p == S->n2) {
+        if (fused_on && pc >= fk->W) {
             S->fused_ki = TileKernelInfo{reinterpret_cast<void (*)(const TileParams)>(fk->fn), fk->L, fk->R, fk->W, fk->threads,
                                          fk->smem_bytes, 1};
             bool ok = true;
