@@ -352,8 +352,9 @@ def test_error_codes_on_device(L):
     assert lib.fftb200_destroy(h) == 0
     assert lib.fftb200_destroy(h) == L.INVALID_PLAN                                      # double destroy: no crash
     assert lib.fftb200_exec_z2z(h, buf.data_ptr(), buf.data_ptr(), -1) == L.INVALID_PLAN
-    hr = L.plan_many(1, [64], None, 0, 0, None, 0, 0, L.D2Z, 1)
-    assert lib.fftb200_exec_d2z(hr, buf.data_ptr(), buf.data_ptr()) == L.INVALID_VALUE     # r2c in place unsupported
+    hr = L.plan_many(2, [8, 64], None, 0, 0, None, 0, 0, L.D2Z, 1)
+    big = torch.zeros(8 * 66, dtype=torch.float64, device="cuda")
+    assert lib.fftb200_exec_d2z(hr, big.data_ptr(), big.data_ptr()) == L.INVALID_VALUE     # r2c in place needs padded rows
     L.destroy(hr)
 
 
@@ -810,7 +811,7 @@ def test_large_prime_lengths_use_bluestein(L, oracle):
     """Lengths with a prime factor above 31 run as Bluestein convolutions through the power-of-two tile passes
     (fftw-3.3.8/dft/bluestein.c is the CPU path's counterpart) instead of O(L * p) radix-p stages; small primes
     (the reference's own 3, 5, {3,3,2}: test/fft_test.rg:143,247,328,349) keep the radix stages."""
-    for kind, shape in [("z2z", (1021,)), ("z2z", (2039,)), ("z2z", (4099,)), ("c2c", (8191,)), ("d2z", (1021,)),
+    for kind, shape in [("z2z", (1021,)), ("z2z", (2039,)), ("z2z", (4093,)), ("c2c", (8191,)), ("d2z", (1021,)),
                         ("z2z", (4, 521)), ("z2z", (97, 6)), ("z2z", (5, 67, 3)), ("r2c", (3, 1009)), ("z2z", (2 * 127, 4))]:
         _, dt_in, _ = _kinds(L)[kind]
         x = oracle.synth(shape, dt_in, 990 + len(shape))
