@@ -197,6 +197,7 @@ bool add_tile_pass_with(Builder &B, const TileKernelInfo *ki, int variant, int L
     tp.in_ls = in_ls;
     tp.out_ls = out_ls;
     tp.n_inner = (int)lv[0].n;
+    tp.n_inner_last_o2 = 0;
     tp.in_is = lv[0].is;
     tp.out_is = lv[0].os;
     tp.n_o2 = (int)lv[1].n;
@@ -389,7 +390,7 @@ static bool build_fast(Builder &B) {
     // 2.21 -> 2.10 ms.  Costs one work buffer of the transform's size; FFTB200_ZBLOCK=0 (or a failed allocation)
     // keeps the in-place three-pass plan.
     // Real transforms (n2c = n2/2+1 columns, not a multiple of the tile width) get the same layout with a ragged last
-    // column block, run as a separate small launch per pass (1024^3 D2Z last pass 4.70 -> see profiles/).
+    // column block (1024^3 D2Z last pass 4.70 -> 3.8 ms).
     if (env_int_or("FFTB200_ZBLOCK", 1) != 0 && rank == 3 && P->batch == 1 && !first && n[0] > 1 && n[1] > 1) {
         const TileKernelInfo *k1 = find_tile_kernel(P->prec, V_CC, (int)n[1]);
         const TileKernelInfo *k0 = find_tile_kernel(P->prec, V_CC, (int)n[0]);
@@ -409,28 +410,27 @@ static bool build_fast(Builder &B) {
                 P->work_bytes = wbytes;
                 // W element (z, y, x) at ((y * nxb + x / Wt) * n0 + z) * Wt + x % Wt
                 const long long w_y = nxb * n[0] * Wt, w_xb = n[0] * Wt, w_z = Wt;
+                // a ragged last column block (real transforms: nx = n2/2+1) is part of the same launch: its tiles load
+                // only their valid lines (clamped) and store only those (TileParams::n_inner_last_o2)
+                auto mark_ragged = [&](void) {
+                    Launch &ln = P->launches.back();
+                    if (rag) {
+                        ln.tp.n_inner_last_o2 = (int)rag;
+                        ln.algo_bytes = ln.algo_bytes / (unsigned long long)(nxb * Wt) * (unsigned long long)nx;
+                    }
+                };
                 bool ok = true;
                 {   // middle axis: natural layout -> blocked work buffer
-                    std::vector<Level> lv1 = {{Wt, 1, 1}, {nxb_full, Wt, w_xb}, {n[0], P->out_stride[1], w_z}};
+                    std::vector<Level> lv1 = {{Wt, 1, 1}, {nxb, Wt, w_xb}, {n[0], P->out_stride[1], w_z}};
                     ok = ok && add_tile_pass(B, V_CC, (int)n[1], P->out_stride[2], w_y, lv1, BUF_OUT, BUF_WORK0, 0,
                                              "strided axis -> blocked work buffer");
-                    if (ok && rag) {
-                        std::vector<Level> lvr = {{rag, 1, 1}, {n[0], P->out_stride[1], w_z}};
-                        ok = add_tile_pass(B, V_CC, (int)n[1], P->out_stride[2], w_y, lvr, BUF_OUT, BUF_WORK0, 0,
-                                           "strided axis -> blocked work buffer (ragged last column block)");
-                        if (ok) { P->launches.back().in_off = nxb_full * Wt; P->launches.back().out_off = nxb_full * w_xb; }
-                    }
+                    if (ok) mark_ragged();
                 }
                 if (ok) {   // slowest axis: blocked work buffer (every tile one contiguous run) -> natural layout
-                    std::vector<Level> lv0 = {{Wt, 1, 1}, {nxb_full, w_xb, Wt}, {n[1], w_y, P->out_stride[2]}};
+                    std::vector<Level> lv0 = {{Wt, 1, 1}, {nxb, w_xb, Wt}, {n[1], w_y, P->out_stride[2]}};
                     ok = add_tile_pass(B, V_CC, (int)n[0], w_z, P->out_stride[1], lv0, BUF_WORK0, BUF_OUT, 0,
                                        "blocked work buffer -> strided axis");
-                    if (ok && rag) {
-                        std::vector<Level> lvr = {{rag, 1, 1}, {n[1], w_y, P->out_stride[2]}};
-                        ok = add_tile_pass(B, V_CC, (int)n[0], w_z, P->out_stride[1], lvr, BUF_WORK0, BUF_OUT, 0,
-                                           "blocked work buffer -> strided axis (ragged last column block)");
-                        if (ok) { P->launches.back().in_off = nxb_full * w_xb; P->launches.back().out_off = nxb_full * Wt; }
-                    }
+                    if (ok) mark_ragged();
                 }
                 if (ok) {
                     P->inplace_ok = layouts_coincide(P);  // pass 1 is tile-wise in place, the others go through the work buffer

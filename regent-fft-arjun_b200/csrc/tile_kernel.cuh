@@ -64,6 +64,8 @@ struct TileParams {
     int prefetch_tiles;  // > 0: every CTA asks L2 to prefetch the input of tile + prefetch_tiles (the tile the
                          // CTA slot it occupies will run next), decoupling HBM latency from SM occupancy
     int n_inner;   // lines along the inner index
+    int n_inner_last_o2;  // > 0: the last o2 block holds only this many lines (ragged last column block of the blocked
+                          // intermediate layout of real transforms); 0: every block holds n_inner
     int n_o2;      // outer index o = o1*n_o2 + o2
     int tiles_per_outer;
     // divisions by tiles_per_outer / n_o2 as multiply-high + shift (fast_div below): every thread of every tile splits
@@ -269,7 +271,8 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
     constexpr int B = (S > 1) ? R / TR::R_LAST : 1;
     constexpr int RL = (S > 1) ? TR::R_LAST : R;
     const unsigned cmask = p.inverse ? 0x80000000u : 0u;
-    const bool ok = (i0 + wl) < p.n_inner;
+    const int n_inner = (p.n_inner_last_o2 > 0 && o2 == p.n_o2 - 1) ? p.n_inner_last_o2 : p.n_inner;
+    const bool ok = (i0 + wl) < n_inner;
     const long long off = o1 * p.out_os1 + o2 * p.out_os2 + (long long)(i0 + wl) * p.out_is + out_shift;
     C *dst = reinterpret_cast<C *>(p.out) + off;
     if constexpr (VAR == V_CC_TW) {
@@ -395,7 +398,8 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
     {
         // lines past the end of a ragged last tile re-read the last valid line (their results are never stored):
         // no predicates or zero fills on the load path
-        const int wi = min(i0 + w1, p.n_inner - 1);
+        const int n_inner = (p.n_inner_last_o2 > 0 && o2 == p.n_o2 - 1) ? p.n_inner_last_o2 : p.n_inner;
+        const int wi = min(i0 + w1, n_inner - 1);
         const C *src = gin + (long long)wi * p.in_is + (long long)u1 * p.in_ls;
         const long long step = (long long)T_LINE * p.in_ls;
 #pragma unroll
@@ -413,7 +417,8 @@ __device__ __forceinline__ void fft_tile_body(const TileParams &p, const int til
             const int fo = fast_div(ft, p.div_tpo_m, p.div_tpo_s);
             const int fi0 = (ft - fo * p.tiles_per_outer) * W;
             const int fo1 = fast_div(fo, p.div_o2_m, p.div_o2_s), fo2 = fo - fo1 * p.n_o2;
-            if (fi0 + W <= p.n_inner) {  // whole tiles only: never touch addresses past the array
+            // whole tiles only: never touch addresses past the array (a ragged last block is not prefetched)
+            if (fi0 + W <= p.n_inner && !(p.n_inner_last_o2 > 0 && fo2 == p.n_o2 - 1)) {
                 const C *fin = reinterpret_cast<const C *>(p.in) + fo1 * p.in_os1 + fo2 * p.in_os2 + (long long)fi0 * p.in_is;
                 constexpr int ELT = (int)sizeof(C);
                 if constexpr (TR::LOAD_ROW) {
