@@ -307,14 +307,23 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
         // output addresses advance by fixed strides over b and q: two 64-bit adds per store, no multiplies
         const long long step_q = (long long)(kmul * (L / RL)) * p.out_ls, step_b = (long long)(kmul * T_LINE) * p.out_ls;
         C *pb = dst + (long long)(kadd + kmul * ul) * p.out_ls;
+        // fp32 data, short q chains (RL <= 4; 512 = 16*16*2 has RL = 2): the recurrence over b stays in fp64, the step
+        // over q is one fp32 multiplication per point by the twiddle step rounded once - half the fp64 work and half the
+        // fp64 -> fp32 conversions (a slow pipe) of carrying every twiddle in fp64, at the cost of one more fp32 rounding
+        constexpr bool Q_IN_FP32 = sizeof(T) == 4 && RL <= 4;
+        const C sqf = mk<T>((T)sq.x, (T)sq.y);
 #pragma unroll
         for (int b = 0; b < B; ++b) {
             double2 wq = wb;
+            C wqf = mk<T>((T)wb.x, (T)wb.y);
             C *pq = pb;
 #pragma unroll
             for (int q = 0; q < RL; ++q) {
                 C x = v[b * RL + q];
-                if constexpr (sizeof(T) == 4) {
+                if constexpr (Q_IN_FP32) {
+                    x = cmul(x, wqf);
+                    if (q + 1 < RL) wqf = cmul(wqf, sqf);
+                } else if constexpr (sizeof(T) == 4) {
                     // fp32 data: the twiddle is carried in fp64 (recurrence) and rounded once to fp32 for the multiply;
                     // converting the data to fp64 and back instead costs four conversions per point on a slow pipe
                     x = cmul(x, mk<T>((T)wq.x, (T)wq.y));
@@ -326,7 +335,7 @@ __device__ __forceinline__ void tile_store(const cplx<T> *v, const TileParams &p
                 x = conj_if(x, cmask);
                 if (ok) st_data<T>(pq, x);
                 pq += step_q;
-                if (q + 1 < RL) wq = mul(wq, sq);
+                if (!Q_IN_FP32 && q + 1 < RL) wq = mul(wq, sq);
             }
             pb += step_b;
             if (b + 1 < B) {

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N=${1:-2}
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29681 tools/slab_probe2.py z2z:1024:FFTB200_SLAB_EX_CTAS=74 z2z:1024:FFTB200_SLAB_EX_CTAS=98 z2z:1024:FFTB200_SLAB_EX_CTAS=120 z2z:1024:FFTB200_SLAB_FUSED=0 c2c:1024:FFTB200_SLAB_EX_CTAS=98 c2c:1024:FFTB200_SLAB_FUSED=0 > gpurun_out/r02_slab_probe_exonly_n${N}.jsonl 2> gpurun_out/r02_slab_probe_exonly_n${N}.err; echo "probe rc=$?"
+cat gpurun_out/r02_slab_probe_exonly_n${N}.jsonl; tail -n 3 gpurun_out/r02_slab_probe_exonly_n${N}.err
