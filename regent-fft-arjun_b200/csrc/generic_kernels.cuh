@@ -75,6 +75,62 @@ __global__ void gen_scatter_kernel(const cplx<T> *__restrict__ packed, cplx<T> *
     }
 }
 
+// inverse real transforms on the generic path: the packed half spectrum [..][n_last/2+1] of the user's buffer is
+// completed to the full Hermitian array  X[k] = conj(X[-k mod n])  (every index negated), re/im swapped for the backward
+// direction like gen_gather_kernel does, and the real result is the (swapped-back) real part of the complex transform
+template <typename T>
+__global__ void gen_gather_herm_kernel(const cplx<T> *__restrict__ in, cplx<T> *__restrict__ packed, GenLayout lay, long long total) {
+    const long long n_last = lay.n[lay.nd - 1], half = n_last / 2;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        long long idx[4] = {0, 0, 0, 0};
+        long long rem = e;
+#pragma unroll
+        for (int d = 3; d >= 0; --d) {
+            if (d < lay.nd) {
+                const long long q = rem / lay.n[d];
+                idx[d] = rem - q * lay.n[d];
+                rem = q;
+            }
+        }
+        const bool mirror = idx[lay.nd - 1] > half;
+        long long off = 0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            if (d < lay.nd) {
+                long long j = idx[d];
+                if (mirror && d > 0) j = (lay.n[d] - j) % lay.n[d];  // (d == 0 is the batch index)
+                off += j * lay.stride[d];
+            }
+        }
+        const T *q = reinterpret_cast<const T *>(in) + 2 * off;
+        cplx<T> x;
+        x.x = q[0];
+        x.y = mirror ? -q[1] : q[1];
+        cplx<T> r;
+        r.x = x.y;  // swap: backward transform through the forward stages
+        r.y = x.x;
+        packed[e] = r;
+    }
+}
+
+template <typename T>
+__global__ void gen_scatter_real_kernel(const cplx<T> *__restrict__ packed, T *__restrict__ out, GenLayout lay, long long total) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        long long rem = e, off = 0;
+#pragma unroll
+        for (int d = 3; d >= 0; --d) {
+            if (d < lay.nd) {
+                const long long q = rem / lay.n[d];
+                off += (rem - q * lay.n[d]) * lay.stride[d];
+                rem = q;
+            }
+        }
+        out[off] = packed[e].y;  // real part after swapping back
+    }
+}
+
 // in-place scaling of the elements of a layout (normalisation helper); COMPONENTS = 2 for complex, 1 for real elements
 template <typename T, int COMPONENTS>
 __global__ void gen_scale_kernel(T *__restrict__ data, GenLayout lay, long long total, T factor) {

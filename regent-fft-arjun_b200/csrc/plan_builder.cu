@@ -645,7 +645,7 @@ static bool build_generic(Builder &B) {
     P->inplace_ok = true;
 
     Launch g;
-    g.kind = Launch::GEN_GATHER;
+    g.kind = P->c2r ? Launch::GEN_GATHER_HERM : Launch::GEN_GATHER;
     g.real_in = P->real;
     g.lay.nd = rank + 1;
     g.lay.n[0] = P->batch;
@@ -656,7 +656,7 @@ static bool build_generic(Builder &B) {
     g.dst = BUF_WORK0;
     g.grid = grid_for(total_in);
     g.algo_bytes = (unsigned long long)total_in * (P->elt_in() + ce);
-    g.desc = "generic gather (user layout -> packed complex)";
+    g.desc = P->c2r ? "generic gather (half spectrum -> full Hermitian array, packed)" : "generic gather (user layout -> packed complex)";
     P->launches.push_back(g);
 
     int cur = BUF_WORK0;
@@ -717,7 +717,7 @@ static bool build_generic(Builder &B) {
         }
     }
     Launch s;
-    s.kind = Launch::GEN_SCATTER;
+    s.kind = P->c2r ? Launch::GEN_SCATTER_REAL : Launch::GEN_SCATTER;
     s.lay.nd = rank + 1;
     s.lay.n[0] = P->batch;
     s.lay.stride[0] = P->out_stride[0];
@@ -728,7 +728,7 @@ static bool build_generic(Builder &B) {
     s.dst = BUF_OUT;
     s.grid = grid_for(total_out);
     s.algo_bytes = (unsigned long long)total_out * ce * 2ull;
-    s.desc = "generic scatter (packed complex -> user layout)";
+    s.desc = P->c2r ? "generic scatter (real part -> user layout)" : "generic scatter (packed complex -> user layout)";
     P->launches.push_back(s);
     return B.err == FFTB200_SUCCESS;
 }
@@ -764,16 +764,8 @@ int create_plan(Plan **out, int rank, const long long *n, int batch, const long 
     Builder B;
     B.P = P.get();
     bool ok = false;
-    if (P->c2r) {
-        if (!build_c2r(B)) {
-            free_plan_resources(P.get());
-            return B.err != FFTB200_SUCCESS ? B.err : FFTB200_UNSUPPORTED;  // power-of-two, unit-stride layouts only
-        }
-        *out = P.release();
-        return FFTB200_SUCCESS;
-    }
     if (!force_generic) {
-        ok = build_fast(B);
+        ok = P->c2r ? build_c2r(B) : build_fast(B);  // (c2r: power-of-two, unit-stride layouts; anything else below)
         if (!ok) {
             // discard partial fast plan
             P->launches.clear();

@@ -113,6 +113,12 @@ template <typename T> static cudaError_t launch_generic(const Launch &ln, const 
         case Launch::GEN_SCATTER:
             gen_scatter_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.lay, ln.total, inverse);
             break;
+        case Launch::GEN_GATHER_HERM:
+            gen_gather_herm_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.lay, ln.total);
+            break;
+        case Launch::GEN_SCATTER_REAL:
+            gen_scatter_real_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (T *)dst, ln.lay, ln.total);
+            break;
         case Launch::BLU_PRE:
             gen_blu_pre_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.chirp, ln.outer, ln.L, ln.M, ln.inner);
             break;
@@ -190,7 +196,6 @@ int exec_plan(Plan *P, const void *in, void *out, int direction) {
         const size_t a_in = P->real ? 2 * P->elt_in() : P->elt_in();
         const size_t a_out = P->c2r ? 2 * P->elt_out() : P->elt_out();
         if ((!host_in && ((uintptr_t)in % a_in)) || (!host_out && ((uintptr_t)out % a_out))) {
-            if (P->c2r) return FFTB200_INVALID_VALUE;  // no generic path for inverse real transforms
             return exec_fallback(P, in, out, direction);
         }
     }

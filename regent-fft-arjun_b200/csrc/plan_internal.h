@@ -19,7 +19,7 @@ namespace fftb200 {
 enum BufSel { BUF_IN = 0, BUF_OUT = 1, BUF_WORK0 = 2, BUF_WORK1 = 3, BUF_BLU = 4 };
 
 struct Launch {
-    enum Kind { TILE, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER, BLU_PRE, BLU_MUL, BLU_POST } kind = TILE;
+    enum Kind { TILE, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER, BLU_PRE, BLU_MUL, BLU_POST, GEN_GATHER_HERM, GEN_SCATTER_REAL } kind = TILE;
     // TILE
     const TileKernelInfo *ki = nullptr;
     TileParams tp{};

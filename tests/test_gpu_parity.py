@@ -802,9 +802,27 @@ def test_inverse_real_transforms(L, oracle):
     lib = L.lib()
     assert lib.fftb200_exec_d2z(h, Xd.data_ptr(), yd.data_ptr()) == L.INVALID_TYPE
     L.destroy(h)
-    hbad = ctypes.c_ulonglong(0)
-    n3 = (ctypes.c_int * 1)(12)
-    assert lib.fftb200_plan_many(ctypes.byref(hbad), 1, n3, None, 0, 0, None, 0, 0, L.Z2D, 1) == L.UNSUPPORTED   # not 2^k
+    # sizes that are not powers of two (odd last dimensions included) take the generic path: Hermitian completion of the
+    # half spectrum, backward complex stages (Bluestein for large primes), real part out
+    for i, (kind, shape) in enumerate([("z2d", (12,)), ("z2d", (12, 10)), ("c2r", (3, 5, 6)), ("z2d", (1000,)), ("z2d", (7, 33)),
+                                       ("z2d", (5, 4, 9)), ("z2d", (1021,)), ("c2r", (6, 127))]):
+        single = kind == "c2r"
+        rdt, cdt = (np.float32, np.complex64) if single else (np.float64, np.complex128)
+        ftype = L.C2R if single else L.Z2D
+        x = oracle.synth(shape, rdt, 1400 + i)
+        X = np.fft.rfftn(x.astype(np.float64)).astype(cdt)
+        n_total = int(np.prod(shape))
+        Xd = torch.from_numpy(np.ascontiguousarray(X)).cuda()
+        yd = torch.zeros(shape, dtype=_torch_dtype(rdt), device="cuda")
+        h = L.plan_many(len(shape), list(shape), None, 0, 0, None, 0, 0, ftype, 1)
+        L.execute(h, ftype, Xd.data_ptr(), yd.data_ptr())
+        torch.cuda.synchronize()
+        desc = L.describe(h)
+        L.destroy(h)
+        assert "Hermitian" in desc, desc
+        err = oracle.rel_l2(yd.cpu().numpy() / n_total, x.astype(np.float64))
+        assert err <= 2 * oracle.tolerance(n_total, single), (kind, shape, err)
+        assert np.array_equal(Xd.cpu().numpy(), X), "c2r input modified"
 
 
 def test_large_prime_lengths_use_bluestein(L, oracle):
