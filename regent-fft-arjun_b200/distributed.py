@@ -185,6 +185,9 @@ class SlabFFT3D:
         peak = nvlink_peak if bound == "nvlink" else hbm_peak
         return {"bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peak_src + "; NVLink 770 GB/s per direction measured peer copy (B200_PROFILING.md)",
+                # what kernels reach when all 8 GPUs exchange at once (tools/peer_probe.cu, profiles/r02_peer_probe_n8.jsonl)
+                "nvlink_all_to_all_ceiling_GB/s": 645.0,
+                "frac_of_all_to_all_ceiling": (ach / 645.0) if bound == "nvlink" else None,
                 "per_rank": {"hbm_pass_model_bytes": self.local_pass_bytes, "nvlink_bytes_out": self.exchange_bytes_out,
                              "hbm_GB/s": self.local_pass_bytes / t / 1e9, "nvlink_GB/s_out": self.exchange_bytes_out / t / 1e9,
                              "ideal_ms_overlapped": max(hbm_t, nvl_t) * 1e3, "ideal_ms_serial": (hbm_t + nvl_t) * 1e3}}
