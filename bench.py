@@ -147,7 +147,7 @@ def pick_threads(F, all_threads: int) -> int:
 def fftw_engine():
     """(engine, kind): the reference's FFTW compiled from its vendored sources (kind "reference")."""
     import oracle
-    if oracle.have_fftw("ref"):
+    if oracle.have_fftw("ref") and not os.environ.get("FFTB200_BENCH_NO_FFTW"):   # (the variable: exercises the fall-backs)
         return oracle.FFTW.get("ref"), "reference"
     return None, "port"
 
@@ -315,6 +315,31 @@ def direct_bins(x_local, z0: int, shape, bins):
     return acc
 
 
+def sampled_bins_parity(x_local, out_local, rank: int, world: int, shape, count: int, seed: int):
+    """rel-L2 over `count` sampled output bins between the transform's output and fp64 direct sums over the same input.
+    x_local: this rank's planes [n0/world][n1][n2]; out_local: the whole output [n0][n1][n2] when world == 1, else this
+    rank's transposed-out slab [n1/world][n0][n2].  Collective for world > 1."""
+    import torch
+    import torch.distributed as dist
+    n0, n1, n2 = shape
+    bins = pick_bins(shape, count, seed)
+    want = direct_bins(x_local, rank * (n0 // world), shape, bins)
+    got = torch.zeros(len(bins), dtype=torch.complex128, device=x_local.device)
+    n1l = n1 // world
+    for i, (k0, k1, k2) in enumerate(bins):
+        if world == 1:
+            got[i] = out_local[k0, k1, k2]
+        elif k1 // n1l == rank:
+            got[i] = out_local[k1 - rank * n1l, k0, k2]
+    if world > 1:
+        dist.all_reduce(torch.view_as_real(want))
+        dist.all_reduce(torch.view_as_real(got))
+    err = float((torch.linalg.vector_norm(got - want) / torch.linalg.vector_norm(want)).item())
+    tol = 10.0 * math.log2(float(n0) * n1 * n2) * 2.220446049250313e-16
+    return {"rel_l2": err, "tol": tol, "ok": bool(err <= tol), "bins": len(bins),
+            "against": "fp64 direct sums over the same input at %d sampled output bins" % len(bins)}
+
+
 def pick_bins(shape, count: int, seed: int):
     import random
     r = random.Random(seed)
@@ -398,21 +423,7 @@ def run_1024(args, L, fft, rank, world, dev, barrier, stream):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     # ---- sampled bins against fp64 direct sums over the same input
-    bins = pick_bins(shape, 128, 1024)
-    want = direct_bins(x, rank * n0l, shape, bins)
-    got = torch.zeros(len(bins), dtype=torch.complex128, device=dev)
-    if world == 1:
-        for i, (k0, k1, k2) in enumerate(bins):
-            got[i] = y[k0, k1, k2]
-    else:
-        n1l = n // world
-        for i, (k0, k1, k2) in enumerate(bins):
-            if k1 // n1l == rank:
-                got[i] = dplan.out[k1 - rank * n1l, k0, k2]
-        dist.all_reduce(torch.view_as_real(want))
-        dist.all_reduce(torch.view_as_real(got))
-    err = float((torch.linalg.vector_norm(got - want) / torch.linalg.vector_norm(want)).item())
-    tol = 10.0 * math.log2(n ** 3) * 2.220446049250313e-16
+    par = sampled_bins_parity(x, y if world == 1 else dplan.out, rank, world, shape, 128, 1024)
     if h is not None:
         L.destroy(h)
     if dplan is not None:
@@ -421,8 +432,7 @@ def run_1024(args, L, fft, rank, world, dev, barrier, stream):
     return {"workload": "3D C2C complex64 (fp64) 1024^3 forward out-of-place, strong-scaled over %d GPU(s)" % world,
             "ms": ms, "GFLOP/s": flops / (ms * 1e-3) / 1e9, "steps": steps, "warmup": warmup, "plan": desc,
             "pass_model_GB/s_per_gpu": pass_model / world / ms / 1e6,
-            "parity": {"rel_l2": err, "tol": tol, "ok": bool(err <= tol), "bins": len(bins),
-                       "against": "fp64 direct sums over the same input at 128 sampled output bins"}}
+            "parity": par}
 
 
 def run_b200(args, rank: int, world: int, local_rank: int) -> int:
@@ -552,8 +562,13 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> int:
             dist.broadcast(ok, src=0)
             if rank != 0:
                 parity = {"ok": bool(ok.item())}
-        if rank == 0 and parity is None:
-            parity = {"ok": False, "rel_l2": None, "against": "oracle/_ref/libfftw3_ref.so missing: parity NOT checked"}
+        have_fftw = torch.tensor([0 if (rank == 0 and parity is None) else 1], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.broadcast(have_fftw, src=0)
+        if int(have_fftw.item()) == 0:
+            # oracle/_ref did not travel: check 256 sampled bins against fp64 direct sums instead of skipping the check
+            parity = sampled_bins_parity(x, y if world == 1 else dplan.out, rank, world, SHAPE, 256, 512)
+            parity["note"] = "oracle/_ref/libfftw3_ref.so missing: sampled bins instead of the full FFTW comparison"
         torch.cuda.empty_cache()
 
     # ---- e2e: same metric through the C ABI with HOST buffers (H2D + transform + D2H in the timed region) ----
