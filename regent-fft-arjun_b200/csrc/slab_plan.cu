@@ -197,11 +197,18 @@ int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, in
         return code;
     };
     // chunking of the contiguous index (multiples of 16 columns keep every segment >= 128 B).
-    // chunks <= 0: automatic — 4 for single-CTA tiles of at most 64 KiB (measured best on 2 x B200 at 512^3), 1 when
-    // the y-axis pass is a cluster kernel or owns the SM (128 KiB tiles: the overlapped pass could not co-reside)
+    // chunks <= 0: automatic.  Single-CTA tiles of at most 64 KiB: 4 (measured best on 2 x B200 at 512^3), 2 from 8 ranks
+    // on (8 x B200, 512^3 D2Z: 0.358 ms with 2, 0.375 with 4, 0.385 unchunked).  128 KiB tiles, which own their SM (the
+    // exchange pass then runs on two thirds of the SMs): 1, and 2 from 8 ranks on (1024^3 D2Z: 2.23 ms with 2, 2.28
+    // unchunked, 2.27 with 4).  Cluster kernels: 1.
     if (chunks <= 0) {
         const TileKernelInfo *k2 = find_tile_kernel(P->prec, V_CC_PEER, n[1]);
-        chunks = (G > 1 && k2 && k2->cluster == 1 && k2->smem_bytes <= 64 * 1024) ? 4 : 1;
+        const bool single = G > 1 && k2 && k2->cluster == 1;
+        if (!single) chunks = 1;
+        else if (k2->smem_bytes <= 64 * 1024) chunks = G >= 8 ? 2 : 4;
+        else chunks = G >= 8 ? 2 : 1;
+        const int forced = env_int_or("FFTB200_SLAB_COL_CHUNKS", 0);   // A/B runs
+        if (forced > 0) chunks = forced;
     }
     long long cw = (S->n2c + chunks - 1) / chunks;
     cw = (cw + 15) / 16 * 16;
@@ -253,7 +260,11 @@ int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, in
         // The exchange pass is NVLink-bound, not SM-bound: when it is pipelined against the z-axis pass
         // keep it persistent on a bounded number of CTAs so that the HBM-bound pass finds free SMs.
         if (G > 1 && S->J > 1) {
-            const unsigned cap = 148u;
+            // (a 128 KiB tile owns its SM outright - all the shared memory it leaves is too small for the z pass's
+            // tiles and it holds every register - so such a pass leaves a third of the SMs to the overlapped pass)
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P->device);
+            const unsigned cap = ln.ki->smem_bytes > 64 * 1024 ? (unsigned)env_int_or("FFTB200_SLAB_EX_CTAS", sms * 2 / 3) : (unsigned)sms;
             // static tile assignment on purpose: with dynamic tickets (TileParams::ticket) every capped CTA stays
             // resident until the chunk ends and the overlapped pass starves (2 x B200, 512^3: 1.61 vs 1.40 ms)
             if (cap > 0 && ln.grid > cap) ln.grid = std::max(1u, cap / ln.ki->cluster) * ln.ki->cluster;
