@@ -260,6 +260,13 @@ static std::vector<int> split_1d(long long N, int prec) {
     const int k = ilog2ll(N);
     // COL passes want L*W*elt <= 64 KiB with 128-byte segments: L <= 512
     std::vector<int> f;
+    // FFTB200_1D_FACTORS=2 (A/B runs): two factors whatever the length, e.g. 2^27 = 2^13 x 2^14 through the cluster kernel
+    // and a 128 KiB row kernel whose transposing store is 8 bytes wide - measured, see DESIGN.md §7
+    if (env_int_or("FFTB200_1D_FACTORS", 0) == 2 && k <= 28) {
+        const int a = k / 2;
+        f = {1 << a, 1 << (k - a)};
+        return f;
+    }
     if (k <= 18) {
         const int a = k / 2;
         f = {1 << a, 1 << (k - a)};
