@@ -160,6 +160,14 @@ bool add_tile_pass_with(Builder &B, const TileKernelInfo *ki, int variant, int L
                         std::vector<Level> lv, int src, int dst, long long twN, const char *what) {
     Plan *P = B.P;
     if (!ki) return false;
+    {
+        // Load the kernel NOW (CUDA loads kernels lazily, at their first launch, and that load synchronises with the
+        // device): a first launch issued while a hand-shake kernel of a slab plan spins on this GPU would block the host
+        // thread - in a single-process multi-GPU program (Legion) the very thread that still has to launch the peer's
+        // work, i.e. a deadlock until the wait times out.  Seen on 2 x B200 with both plans driven by one thread.
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, (const void *)ki->fn) != cudaSuccess) cudaGetLastError();
+    }
     merge_levels(lv);
     if (lv.size() > 3) return false;
     while (lv.size() < 3) lv.push_back({1, 0, 0});

@@ -9,10 +9,18 @@
 namespace fftb200 {
 
 // one launch of a tile pass; cluster kernels go through cudaLaunchKernelEx with the cluster dimension
+// FFTB200_DEBUG=1: say which CUDA call failed (stderr); the ABI itself only returns codes
+static cudaError_t report(cudaError_t e, const TileKernelInfo *ki, unsigned grid) {
+    if (e != cudaSuccess && getenv("FFTB200_DEBUG"))
+        fprintf(stderr, "libfft_b200: launch of tile kernel L=%d R=%d W=%d cluster=%d grid=%u threads=%d smem=%d failed: %s\n", ki->L, ki->R,
+                ki->W, ki->cluster, grid, ki->threads, ki->smem_bytes, cudaGetErrorString(e));
+    return e;
+}
+
 cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st, const TileParams &tp) {
     if (ki->cluster <= 1) {
         ki->fn<<<grid, ki->threads, ki->smem_bytes, st>>>(tp);
-        return cudaGetLastError();
+        return report(cudaGetLastError(), ki, grid);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid / ki->cluster * ki->cluster, 1, 1);
@@ -27,7 +35,7 @@ cudaError_t launch_tile(const TileKernelInfo *ki, unsigned grid, cudaStream_t st
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, ki->fn, tp);
-    return e != cudaSuccess ? e : cudaGetLastError();
+    return report(e != cudaSuccess ? e : cudaGetLastError(), ki, grid);
 }
 
 void free_plan_resources(Plan *p) {

@@ -26,6 +26,7 @@
 // so the z-axis pass hides under the NVLink transfer of the following chunks.
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -126,6 +127,14 @@ __global__ void slab_wait_kernel(const unsigned long long *flags, int G, int kin
 __global__ void slab_release_all_kernel(SlabPeers peers, int G, int me, unsigned long long epoch) {
     const int d = threadIdx.x & (MAX_PEERS - 1), kind = threadIdx.x / MAX_PEERS;
     if (d < G && kind < 64) st_release_sys(peers.flags[d] + (size_t)kind * MAX_PEERS + me, epoch);
+}
+
+// see add_tile_pass_with: every kernel a slab exec launches is loaded at plan creation
+static void preload_slab_kernels() {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, (const void *)slab_signal_kernel) != cudaSuccess) cudaGetLastError();
+    if (cudaFuncGetAttributes(&fa, (const void *)slab_wait_kernel) != cudaSuccess) cudaGetLastError();
+    if (cudaFuncGetAttributes(&fa, (const void *)slab_release_all_kernel) != cudaSuccess) cudaGetLastError();
 }
 
 void slab_free(Plan *P) {
@@ -411,6 +420,7 @@ int slab_create(Plan **out, const int *n, fftb200_type type, int rank, int G, in
         if (cudaEventCreate(&S->ev_t[i]) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
     S->peer_area[rank] = S->area;
     if (G == 1) S->connected = true;
+    preload_slab_kernels();
     *out = P.release();
     return FFTB200_SUCCESS;
 }
@@ -476,6 +486,7 @@ int slab_create_2d(Plan **out, const int *n, fftb200_type type, int rank, int G)
         if (cudaEventCreate(&S->ev_t[i]) != cudaSuccess) return fail(FFTB200_SETUP_FAILED);
     S->peer_area[rank] = S->area;
     if (G == 1) S->connected = true;
+    preload_slab_kernels();
     *out = P.release();
     return FFTB200_SUCCESS;
 }
@@ -599,7 +610,11 @@ static int slab_exec_p2p_body(Plan *P, const void *in, void *out, int inverse, c
 int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
     SlabState *S = P->slab;
     if (!S->connected) return FFTB200_INVALID_PLAN;
-    if (*reinterpret_cast<volatile int *>(S->err_host) != 0) return FFTB200_EXEC_FAILED;  // an earlier hand-shake timed out
+    if (*reinterpret_cast<volatile int *>(S->err_host) != 0) {  // an earlier hand-shake timed out (1 + flag kind) or failed
+        if (getenv("FFTB200_DEBUG"))
+            fprintf(stderr, "libfft_b200: slab plan of rank %d is poisoned: error word %d (epoch %llu)\n", S->rank, *S->err_host, S->epoch);
+        return FFTB200_EXEC_FAILED;
+    }
     DeviceGuard g(P->device);
     std::lock_guard<std::mutex> lk(P->mu);
     const unsigned long long epoch = ++S->epoch;
@@ -610,6 +625,9 @@ int slab_exec_p2p(Plan *P, const void *in, void *out, int inverse) {
         recv[d] = d < S->G ? S->peer_area[d] : nullptr;
     }
     const int rc = slab_exec_p2p_body(P, in, out, inverse, peers, recv, epoch);
+    if (rc != FFTB200_SUCCESS && getenv("FFTB200_DEBUG"))
+        fprintf(stderr, "libfft_b200: slab exec failed on rank %d (code %d), last CUDA error: %s\n", S->rank, rc,
+                cudaGetErrorString(cudaPeekAtLastError()));
     if (rc != FFTB200_SUCCESS && S->G > 1) {
         // a launch failed in the middle of the collective: publish every flag of this epoch anyway so that the peers'
         // wait kernels terminate (their result is garbage, they learn of it through the caller's error handling),

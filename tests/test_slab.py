@@ -202,3 +202,51 @@ def test_slab_multi_gpu(built, mode):
                         ("c2c", "256,256,256")]:
         _torchrun(world, ["--backend", "nccl", "--engine", "cuda", "--mode", mode, "--kind", kind, "--shape", shape,
                           "--chunks", "4", "--reps", "3"], port=29800 + (7 if mode == "p2p" else 0) + len(shape))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,shape", [("z2z", (128, 128, 128)), ("d2z", (64, 128, 256)), ("z2z", (64, 32, 48 // 3 * 4))])
+def test_slab_single_process_two_gpus(fft, oracle, kind, shape):
+    """The Legion way: ONE process, one plan per GPU created with that GPU current, the exchange areas
+    connected with fftb200_slab_get_area / fftb200_slab_connect_ptrs (peer access, no IPC), both execs issued from the same
+    host thread (they are asynchronous; each GPU's kernels wait for the other's flags on the device)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    L = fft._lib
+    G = 2
+    ftype = {"z2z": L.Z2Z, "d2z": L.D2Z}[kind]
+    np_in = {"z2z": np.complex128, "d2z": np.float64}[kind]
+    real = kind == "d2z"
+    n0, n1, n2 = shape
+    n2c = n2 // 2 + 1 if real else n2
+    full = oracle.synth(shape, np_in, seed=97)
+    plans, xs, outs = [], [], []
+    for r in range(G):
+        with torch.cuda.device(r):
+            plans.append(L.slab_plan(list(shape), ftype, r, G, 0))
+            xs.append(torch.from_numpy(np.ascontiguousarray(full[r * (n0 // G):(r + 1) * (n0 // G)])).cuda(r))
+            outs.append(torch.zeros((n1 // G, n0, n2c), dtype=torch.complex128, device=f"cuda:{r}"))
+    areas = [L.slab_area(h)[0] for h in plans]
+    for r in range(G):
+        with torch.cuda.device(r):
+            L.slab_connect_ptrs(plans[r], areas)
+    for rep in range(3):
+        for r in range(G):
+            with torch.cuda.device(r):
+                L.set_stream(plans[r], torch.cuda.current_stream(r).cuda_stream)
+                L.slab_exec(plans[r], xs[r].data_ptr(), outs[r].data_ptr())
+    for r in range(G):
+        torch.cuda.synchronize(r)
+    from regent_fft_arjun_b200 import distributed as D
+    got = D.assemble_transposed([o.cpu().numpy() for o in outs])
+    for r in range(G):      # no rank frees its exchange area while the peer could still store into it
+        torch.cuda.synchronize(r)
+    for r in range(G):
+        with torch.cuda.device(r):
+            L.destroy(plans[r])
+    F = oracle.FFTW.get("ref") if oracle.have_fftw("ref") else None
+    x64 = full.astype(np.float64 if real else np.complex128)
+    want = (F.r2c(x64) if real else F.dft(x64)) if F else (oracle.port_r2c(x64) if real else oracle.port_dft(x64))
+    assert oracle.rel_l2(got, want) <= oracle.tolerance(int(np.prod(shape)), False), (kind, shape)
+    for r in range(G):
+        assert np.array_equal(xs[r].cpu().numpy(), full[r * (n0 // G):(r + 1) * (n0 // G)]), "input slab modified"
