@@ -556,7 +556,20 @@ static const int BLUESTEIN_MIN_PRIME = 31;
 // The convolution runs through BUF_BLU ([outer][M][inner], M = 2^m >= 2L-1) with the library's own power-of-two tile
 // passes (forward, pointwise product with the transformed chirp, backward).  Returns false (nothing added) when M does
 // not fit a single tile pass; the caller then falls back to the radix-p stages.
+static bool add_bluestein_axis_impl(Builder &B, int *cur, int axis, long long outer, int L, long long inner);
+
 static bool add_bluestein_axis(Builder &B, int *cur, int axis, long long outer, int L, long long inner) {
+    // all or nothing: a failure half-way must not leave some of the axis's launches behind (the caller falls back to
+    // the radix-p stages)
+    const size_t n_launches = B.P->launches.size();
+    const int cur0 = *cur;
+    if (add_bluestein_axis_impl(B, cur, axis, outer, L, inner)) return true;
+    B.P->launches.resize(n_launches);
+    *cur = cur0;
+    return false;
+}
+
+static bool add_bluestein_axis_impl(Builder &B, int *cur, int axis, long long outer, int L, long long inner) {
     Plan *P = B.P;
     int M = 1;
     while (M < 2 * L - 1) M *= 2;

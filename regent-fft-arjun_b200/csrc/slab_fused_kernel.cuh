@@ -102,7 +102,7 @@ fft_slab_fused_kernel(const SlabFusedParams p) {
     // always before it waits for anything.
     const bool ex_role = blockIdx.x < (gridDim.x + 1) / 2;
     bool ex_open = true, loc_open = true, peers_free = false, x_all_done = false;
-    unsigned ready_mask = 0;                       // chunks whose arrival this CTA has already observed
+    unsigned long long ready_mask = 0;             // chunks (< 64) whose arrival this CTA has already observed
     int pend_kind = 0, pend_chunk = 0;             // 1 = Y tiles, 2 = X tiles finished but not yet published
     unsigned pend_count = 0;
     auto flush = [&]() {
@@ -148,11 +148,11 @@ fft_slab_fused_kernel(const SlabFusedParams p) {
             if (ticket < J * per_x) {
                 const int chunk = ticket / per_x, t = ticket - chunk * per_x;
                 if (pend_kind != 0 && pend_kind != 2) flush();
-                if (!((ready_mask >> chunk) & 1u)) {
+                if (!((ready_mask >> chunk) & 1ull)) {
                     flush();  // never wait with unpublished work
                     if (threadIdx.x == 0) fused_wait_peers(p, 1 + chunk);  // (G == 1: my own flag, set by my last Y tile)
                     __syncthreads();
-                    ready_mask |= 1u << chunk;
+                    ready_mask |= 1ull << chunk;
                 }
                 const long long sh = (long long)chunk * p.x_chunk_shift;
                 fft_tile_body<T, L, R, W, V_RR, true>(p.x, t, smem_raw, sh, sh);
