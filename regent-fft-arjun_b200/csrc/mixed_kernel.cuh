@@ -1,0 +1,154 @@
+// mixed_kernel.cuh — one-pass-per-axis shared-memory FFT for lengths that are NOT powers of two:
+// L = 2^a 3^b 5^c 7^d (96, 100, 120, 360, 384, 480, 1000, 1536, 6000, ...).
+//
+// The power-of-two tile kernels (tile_kernel.cuh) keep R points per thread in registers across all stages and are tuned to
+// the HBM roofline; this kernel is the general form of the same idea for the sizes they do not cover.  A CTA loads a tile
+// of W lines of length L, runs one Stockham autosort stage per radix - the first reading global memory, the last writing
+// it, the exchanges in between through shared memory - and so makes one HBM round trip per axis instead of the generic
+// path's gather + one global-memory pass per prime factor + scatter.  The radices are the in-register DFTs of radix_dft.cuh (2 ... 16,
+// products of 2, 3, 5, 7), chosen at plan time so that a line needs as few stages as possible (1000 = 10 x 10 x 10,
+// 384 = 6 x 8 x 8, 96 = 12 x 8); every stage has its own twiddle table, laid out so that a warp reads it as contiguous
+// runs.  The reference's CPU path covers these sizes with FFTW's n1_3 / n1_5 / n1_7 / ... codelets and its generic
+// Cooley-Tukey solver (fftw-3.3.8/dft/ct.c, dft/scalar/codelets/); its own test shapes 3, 5, {3,2,2}, {3,3,2}
+// (test/fft_test.rg:143,247,328,349) are of this kind.
+//
+// Stage s (radix P, Ns = product of the earlier radices, Lp = L / P), butterfly j in [0, Lp):
+//     k = j mod Ns;   a_t = x[j + t Lp] * w_L^(t k L / (Ns P)),  t in [0, P);   y[(j - k) P + k + q Ns] = DFT_P(a)[q]
+//
+// Addressing and tiling are TileParams' (tile_kernel.cuh): in[o1*in_os1 + o2*in_os2 + i*in_is + l*in_ls].
+//   ROWMAP = true   contiguous axis (in_ls == out_ls == 1): nfast threads run along a line, the other thread index
+//                   picks the line; shared layout [w][pitch] (pitch odd: lanes of one warp may span several lines)
+//   ROWMAP = false  strided axis (in_is == out_is == 1): the W adjacent lines are the fast thread index; shared layout
+//                   [l][W]
+#pragma once
+#include "radix_dft.cuh"
+#include "tile_kernel.cuh"
+
+namespace fftb200 {
+
+constexpr int MIXED_MAX_STAGES = 8;
+constexpr int MIXED_MAX_THREADS = 256;
+
+struct MixedStages {
+    int n;          // number of stages
+    int L, W;       // line length, lines per tile
+    int nfast;      // ROWMAP: threads along a line; else W (the adjacent lines are the fast thread index)
+    int nslow;      // blockDim.x / nfast
+    int pitch;      // ROWMAP: shared-memory elements between consecutive lines of the tile
+    unsigned char r[MIXED_MAX_STAGES];   // radix of each stage, product = L
+    int tw_off[MIXED_MAX_STAGES];        // stage s: table at tw + tw_off[s], entry [(t-1)*Ns + k] = w_L^(t k L / (Ns P))
+    unsigned ns_m[MIXED_MAX_STAGES], ns_s[MIXED_MAX_STAGES];  // fast_div constants of Ns
+};
+
+// One Stockham stage of radix P over the tile.  The first stage reads its points straight from global memory and the last
+// one stores straight to it (both coalesced: for a fixed t consecutive butterflies touch consecutive elements), so only
+// the exchanges between stages go through shared memory.
+//   SRC_G / DST_G: source / destination is global memory (strides in TileParams) instead of shared memory
+template <typename T, int P, bool ROWMAP, bool SRC_G, bool DST_G>
+__device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStages &ms, const cplx<T> *__restrict__ gin,
+                                            cplx<T> *__restrict__ gout, const cplx<T> *__restrict__ ssrc,
+                                            cplx<T> *__restrict__ sdst, const cplx<T> *__restrict__ tws, const int Ns,
+                                            const unsigned nm, const unsigned nsh, const int i0, const int f, const int sl,
+                                            const unsigned cmask) {
+    using C = cplx<T>;
+    const int Lp = ms.L / P;
+    const int W = ms.W;
+    // ROWMAP: f runs over the butterflies of a line, sl over the lines; otherwise f is the line, sl the butterfly
+    const int j0 = ROWMAP ? f : sl, jstep = ROWMAP ? ms.nfast : ms.nslow;
+    const int w0 = ROWMAP ? sl : f, wstep = ROWMAP ? ms.nslow : W;
+    const int s_line = ROWMAP ? ms.pitch : 1, s_elem = ROWMAP ? 1 : W;  // shared index = w * s_line + l * s_elem
+    for (int j = j0; j < Lp; j += jstep) {
+        const int q = fast_div(j, nm, nsh), k = j - q * Ns;
+        const int ob = j + q * Ns * (P - 1);
+        for (int w = w0; w < W; w += wstep) {
+            C a[P];
+            if (SRC_G) {
+                const int wi = min(i0 + w, p.n_inner - 1);  // (a ragged last tile re-reads its last valid line; never stored)
+                const C *g = gin + (long long)wi * p.in_is + (long long)j * p.in_ls;
+                const long long st = (long long)Lp * p.in_ls;
+#pragma unroll
+                for (int t = 0; t < P; ++t) a[t] = conj_if(__ldg(g + t * st), cmask);
+            } else {
+                const C *s = ssrc + w * s_line + j * s_elem;
+#pragma unroll
+                for (int t = 0; t < P; ++t) a[t] = s[t * Lp * s_elem];
+            }
+            if (Ns > 1) {
+#pragma unroll
+                for (int t = 1; t < P; ++t) a[t] = cmul(a[t], __ldg(tws + (t - 1) * Ns + k));
+            }
+            Dft<T, P>::run(a);
+            if (DST_G) {
+                if (i0 + w < p.n_inner) {
+                    C *g = gout + (long long)(i0 + w) * p.out_is + (long long)ob * p.out_ls;
+                    const long long st = (long long)Ns * p.out_ls;
+#pragma unroll
+                    for (int t = 0; t < P; ++t) g[t * st] = conj_if(a[t], cmask);
+                }
+            } else {
+                C *d = sdst + w * s_line + ob * s_elem;
+#pragma unroll
+                for (int t = 0; t < P; ++t) d[t * Ns * s_elem] = a[t];
+            }
+        }
+    }
+}
+
+template <typename T, bool ROWMAP, int MAXR>
+__global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const TileParams p, const MixedStages ms) {
+    using C = cplx<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = ms.L, W = ms.W;
+    const size_t buf_elems = ROWMAP ? (size_t)W * ms.pitch : (size_t)W * L;
+    C *buf0 = reinterpret_cast<C *>(smem_raw);
+    C *buf1 = buf0 + buf_elems;  // (present when the line needs three stages or more)
+    const int tile = (int)blockIdx.x;
+    const int o = fast_div(tile, p.div_tpo_m, p.div_tpo_s);
+    const int i0 = (tile - o * p.tiles_per_outer) * W;
+    const int o1 = fast_div(o, p.div_o2_m, p.div_o2_s), o2 = o - o1 * p.n_o2;
+    const C *__restrict__ gin = reinterpret_cast<const C *>(p.in) + o1 * p.in_os1 + o2 * p.in_os2;
+    C *__restrict__ gout = reinterpret_cast<C *>(p.out) + o1 * p.out_os1 + o2 * p.out_os2;
+    const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);
+    const unsigned cmask = p.inverse ? 0x80000000u : 0u;
+    int sl = (int)threadIdx.x / ms.nfast;
+    const int f = (int)threadIdx.x - sl * ms.nfast;
+    if (sl >= ms.nslow) sl = 1 << 30;  // threads past nfast * nslow (block rounded up to whole warps) only take part in the barriers
+
+    C *src = buf0, *dst = buf0;
+    int Ns = 1;
+    for (int s = 0; s < ms.n; ++s) {
+        const int P = ms.r[s];
+        const C *tws = tw + ms.tw_off[s];
+        const unsigned nm = ms.ns_m[s], nsh = ms.ns_s[s];
+        const bool first = s == 0, last = s == ms.n - 1;
+#define FFTB200_MIXED_CASE(R)                                                                                        \
+    case R:                                                                                                          \
+        if constexpr (R <= MAXR) {                                                                                   \
+            if (first && last) mixed_stage<T, R, ROWMAP, true, true>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);        \
+            else if (first) mixed_stage<T, R, ROWMAP, true, false>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);     \
+            else if (last) mixed_stage<T, R, ROWMAP, false, true>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);      \
+            else mixed_stage<T, R, ROWMAP, false, false>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);               \
+        }                                                                                                            \
+        break;
+        switch (P) {
+            FFTB200_MIXED_CASE(2) FFTB200_MIXED_CASE(3) FFTB200_MIXED_CASE(4) FFTB200_MIXED_CASE(5) FFTB200_MIXED_CASE(6)
+            FFTB200_MIXED_CASE(7) FFTB200_MIXED_CASE(8) FFTB200_MIXED_CASE(9) FFTB200_MIXED_CASE(10) FFTB200_MIXED_CASE(12)
+            FFTB200_MIXED_CASE(14) FFTB200_MIXED_CASE(15) FFTB200_MIXED_CASE(16)
+            default: break;
+        }
+#undef FFTB200_MIXED_CASE
+        Ns *= P;
+        if (!last) __syncthreads();
+        // stage s wrote dst; the next one reads it and writes the other buffer
+        src = dst;
+        dst = (dst == buf0) ? buf1 : buf0;
+    }
+}
+
+// host side: the instantiations (precision x mapping x largest radix compiled in: 8, 10 or 16 - the register count follows
+// the largest in-register DFT); radices the kernel has code for
+typedef void (*MixedKernelFn)(const TileParams, const MixedStages);
+MixedKernelFn mixed_kernel(int prec, bool rowmap, int maxr);
+constexpr int MIXED_RADICES[] = {16, 15, 14, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+
+}  // namespace fftb200

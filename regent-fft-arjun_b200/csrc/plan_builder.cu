@@ -12,6 +12,9 @@
 //   anything else         : generic global-memory path (generic_kernels.cuh)
 //
 // No CPU fallback exists: if a kernel cannot be launched the call returns an error code.
+#include <algorithm>
+#include <functional>
+#include <tuple>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -475,6 +478,225 @@ static bool build_fast(Builder &B) {
 }
 
 // ------------------------------------------------------------------------------------------
+// mixed-radix plan: complex transforms with unit element stride whose axes are products of 2, 3, 5 and 7 that fit one
+// shared-memory tile (mixed_kernel.cuh).  One kernel per axis, in place over the output array like the fast plan;
+// power-of-two axes of such a shape still use the tuned tile kernels.  Anything else goes to the generic path.
+// ------------------------------------------------------------------------------------------
+// L as a product of the radices the kernel has in-register DFTs for (all <= maxr): fewest stages, then the smallest
+// largest radix, then the smallest sum.  Empty when L has another prime factor.
+static std::vector<int> mixed_radices(long long L, int maxr) {
+    struct Best { int stages = 1 << 20, maxr = 0, sum = 0; std::vector<int> r; };
+    std::map<long long, Best> memo;
+    std::function<const Best &(long long)> go = [&](long long v) -> const Best & {
+        auto it = memo.find(v);
+        if (it != memo.end()) return it->second;
+        Best best;
+        if (v == 1) {
+            best.stages = 0;
+        } else {
+            for (int r : MIXED_RADICES) {
+                if (r > maxr || v % r) continue;
+                const Best &sub = go(v / r);
+                if (sub.stages >= (1 << 20)) continue;
+                Best c;
+                c.stages = sub.stages + 1;
+                c.maxr = std::max(sub.maxr, r);
+                c.sum = sub.sum + r;
+                if (std::make_tuple(c.stages, c.maxr, c.sum) < std::make_tuple(best.stages, best.maxr, best.sum)) {
+                    c.r = sub.r;
+                    c.r.push_back(r);
+                    best = c;
+                }
+            }
+        }
+        return memo[v] = best;
+    };
+    std::vector<int> r = go(L).r;
+    // the first stage stores with a stride of its radix: odd radices first (conflict-free), powers of two last
+    auto cls = [](int v) { return (v & 1) ? 0 : ((v & (v - 1)) ? 1 : 2); };
+    std::stable_sort(r.begin(), r.end(), [&](int x, int y) { return cls(x) < cls(y); });
+    return r;
+}
+
+static const size_t MIXED_SMEM_MAX = 200u << 10;
+
+static int mixed_max_radix(int prec) {
+    // largest in-register DFT: the register count of the kernel follows it (fp64: radix 16 needs 138 registers)
+    const int dflt = prec ? 10 : 16;
+    const int v = env_int_or("FFTB200_MIXED_MAXR", dflt);
+    return v <= 8 ? 8 : (v <= 10 ? 10 : 16);
+}
+
+static bool mixed_axis_ok(long long L, int prec) {
+    if (L < 2 || L > 0x7fffff) return false;
+    const std::vector<int> r = mixed_radices(L, mixed_max_radix(prec));
+    const size_t nbuf = r.size() >= 3 ? 2 : 1;
+    return !r.empty() && (int)r.size() <= MIXED_MAX_STAGES && nbuf * (size_t)(L + 1) * (prec ? 16 : 8) <= MIXED_SMEM_MAX;
+}
+
+static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long long out_ls, std::vector<Level> lv, int src,
+                           int dst, const char *what) {
+    Plan *P = B.P;
+    const size_t ce = P->prec ? 16 : 8;
+    const int maxr = mixed_max_radix(P->prec);
+    const std::vector<int> rad = mixed_radices(L, maxr);
+    if (rad.empty() || (int)rad.size() > MIXED_MAX_STAGES) return false;
+    MixedStages ms{};
+    ms.n = (int)rad.size();
+    ms.L = L;
+    const long long lines0 = lv.empty() ? 1 : std::max<long long>(1, lv[0].n);
+    const size_t budget = (size_t)env_int_or("FFTB200_MIXED_TILE_KB", 16) << 10;  // one shared-memory buffer
+    const int nbuf = ms.n >= 3 ? 2 : (ms.n == 2 ? 1 : 0);  // exchanges between stages: ping-pong from three stages on
+    int W, threads;
+    if (row) {
+        // threads along a line: the count that wastes the fewest thread slots over the stages (stage s has L / r_s
+        // butterflies per line); the rest of the CTA takes further lines
+        int lp_max = 0;
+        for (int r : rad) lp_max = std::max(lp_max, L / r);
+        const int hi = std::min(lp_max, MIXED_MAX_THREADS), lo = std::min(hi, 32);
+        long long best_cost = -1;
+        int tl = hi;
+        for (int c = lo; c <= hi; ++c) {
+            long long cost = 0;
+            for (int r : rad) cost += (long long)((L / r + c - 1) / c) * c;
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; tl = c; }
+        }
+        ms.pitch = L | 1;  // odd: threads of one warp that sit on different lines hit different banks
+        int nslow = (int)std::min<long long>(std::max(1, MIXED_MAX_THREADS / tl), lines0);
+        const size_t line_bytes = (size_t)ms.pitch * ce;
+        int rounds = (int)std::max<size_t>(1, budget / (line_bytes * nslow));
+        while (nslow > 1 && (size_t)std::max(1, nbuf) * nslow * line_bytes > MIXED_SMEM_MAX) --nslow;
+        rounds = (int)std::min<long long>(rounds, std::max<long long>(1, lines0 / nslow));
+        while (rounds > 1 && (size_t)std::max(1, nbuf) * nslow * rounds * line_bytes > MIXED_SMEM_MAX) --rounds;
+        W = nslow * rounds;
+        ms.nfast = tl;
+        ms.nslow = nslow;
+        threads = (tl * nslow + 31) / 32 * 32;
+    } else {
+        W = (int)(128 / ce);  // one 128-byte segment per line position
+        while (W > 1 && (size_t)std::max(1, nbuf) * L * W * ce > MIXED_SMEM_MAX) W /= 2;
+        ms.nfast = W;
+        ms.pitch = 0;
+        // enough butterfly slots for the widest stage, in whole warps
+        int lp_max = 0;
+        for (int r : rad) lp_max = std::max(lp_max, L / r);
+        int nslow = 1;
+        while (nslow * 2 * W <= MIXED_MAX_THREADS && nslow < lp_max) nslow *= 2;
+        while (nslow * W < 32) nslow *= 2;
+        ms.nslow = nslow;
+        threads = nslow * W;
+    }
+    ms.W = W;
+    const size_t smem = (size_t)nbuf * ce * (row ? (size_t)W * ms.pitch : (size_t)W * L);
+    if (smem > MIXED_SMEM_MAX) return false;
+    // per-stage twiddle tables: stage s (radix p, Ns = product of the earlier radices) reads entry [(t-1)*Ns + k] =
+    // w_L^(t k L / (Ns p)), t in [1, p), k in [0, Ns): consecutive butterflies read consecutive entries
+    std::vector<double> tw;
+    {
+        long long Ns = 1;
+        for (int s = 0; s < ms.n; ++s) {
+            const int p = rad[s];
+            ms.r[s] = (unsigned char)p;
+            ms.tw_off[s] = (int)(tw.size() / 2);
+            fast_div_make((int)Ns, &ms.ns_m[s], &ms.ns_s[s]);
+            if (Ns > 1) {
+                const long long step = L / (Ns * p);
+                for (int t = 1; t < p; ++t)
+                    for (long long k = 0; k < Ns; ++k) {
+                        double re, im;
+                        twiddle((t * k * step) % L, L, &re, &im);
+                        tw.push_back(re);
+                        tw.push_back(im);
+                    }
+            }
+            Ns *= p;
+        }
+        if (tw.empty()) { tw.push_back(1.0); tw.push_back(0.0); }
+    }
+    void *dtw;
+    if (P->prec) {
+        dtw = B.upload(tw.data(), tw.size() * sizeof(double));
+    } else {
+        std::vector<float> twf(tw.begin(), tw.end());
+        dtw = B.upload(twf.data(), twf.size() * sizeof(float));
+    }
+    if (!dtw) return false;
+    int kmax = 0;
+    for (int r : rad) kmax = std::max(kmax, r);
+    std::unique_ptr<TileKernelInfo> ki(new TileKernelInfo);
+    ki->fn = reinterpret_cast<void (*)(const TileParams)>(mixed_kernel(P->prec, row, kmax));  // (launched with its own signature)
+    ki->L = L;
+    ki->R = L;  // no per-stage tile tables: add_tile_pass_with leaves tp.tw alone
+    ki->W = W;
+    ki->threads = threads;
+    // (the opt-in shared-memory limit is a property of the kernel, shared by every plan: always raise it to the maximum)
+    ki->smem_bytes = (int)MIXED_SMEM_MAX;
+    ki->cluster = 1;
+    if (!add_tile_pass_with(B, ki.get(), row ? V_RR : V_CC, L, in_ls, out_ls, lv, src, dst, 0, what)) return false;
+    ki->smem_bytes = (int)smem;
+    Launch &ln = P->launches.back();
+    ln.kind = Launch::MIXED;
+    ln.mixed = ms;
+    ln.mixed_row = row;
+    ln.tp.tw = dtw;
+    ln.tp.prefetch_tiles = 0;
+    std::string radices;
+    for (int i = 0; i < ms.n; ++i) radices += (i ? "x" : "") + std::to_string((int)ms.r[i]);
+    char buf[256];
+    snprintf(buf, sizeof buf, "mixed-radix %s %s L=%d (%s) W=%d threads=%d (%d along %s) smem=%d tiles=%u (%s)",
+             row ? "row" : "col", P->prec ? "fp64" : "fp32", L, radices.c_str(), W, threads, ms.nfast,
+             row ? "a line" : "the lines", (int)smem, ln.grid, what);
+    ln.desc = buf;
+    P->mixed_infos.push_back(std::move(ki));
+    return B.err == FFTB200_SUCCESS;
+}
+
+static bool build_mixed(Builder &B) {
+    Plan *P = B.P;
+    const int rank = P->rank, last = rank - 1;
+    const long long *n = P->n;
+    if (P->real || P->c2r) return false;
+    if (env_int_or("FFTB200_MIXED", 1) == 0) return false;
+    if (P->in_stride[rank] != 1 || P->out_stride[rank] != 1) return false;
+    const int maxL = max_tile_length(P->prec);
+    long long total = 1;
+    for (int d = 0; d < rank; ++d) {
+        total *= n[d];
+        if (n[d] == 1) continue;
+        if (!(is_pow2(n[d]) && n[d] <= maxL) && !mixed_axis_ok(n[d], P->prec)) return false;
+    }
+    if (total == 1) return false;
+    auto levels_for = [&](int axis, bool first_pass) {
+        std::vector<Level> lv;
+        for (int d = rank - 1; d >= 0; --d) {
+            if (d == axis) continue;
+            lv.push_back({n[d], first_pass ? P->in_stride[d + 1] : P->out_stride[d + 1], P->out_stride[d + 1]});
+        }
+        lv.push_back({P->batch, first_pass ? P->in_stride[0] : P->out_stride[0], P->out_stride[0]});
+        return lv;
+    };
+    bool first = true;
+    for (int axis = last; axis >= 0; --axis) {
+        if (n[axis] == 1) continue;
+        const bool row = axis == last;
+        const long long in_ls = first ? P->in_stride[axis + 1] : P->out_stride[axis + 1];
+        const long long out_ls = P->out_stride[axis + 1];
+        const int src = first ? BUF_IN : BUF_OUT;
+        bool ok;
+        if (is_pow2(n[axis]) && find_tile_kernel(P->prec, row ? V_RR : V_CC, (int)n[axis]))
+            ok = add_tile_pass(B, row ? V_RR : V_CC, (int)n[axis], in_ls, out_ls, levels_for(axis, first), src, BUF_OUT, 0,
+                               row ? "last axis" : "strided axis");
+        else
+            ok = add_mixed_pass(B, row, (int)n[axis], in_ls, out_ls, levels_for(axis, first), src, BUF_OUT,
+                                row ? "last axis" : "strided axis");
+        if (!ok) return false;
+        first = false;
+    }
+    P->inplace_ok = layouts_coincide(P);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
 // inverse real plan (C2R / Z2D): backward COL passes over the n_last/2+1 columns (through a work buffer, so the
 // input survives), then the fused even/odd pre-pass + half-length backward FFT on the last axis
 // ------------------------------------------------------------------------------------------
@@ -793,7 +1015,21 @@ int create_plan(Plan **out, int rank, const long long *n, int batch, const long 
     B.P = P.get();
     bool ok = false;
     if (!force_generic) {
+        auto discard = [&]() {
+            P->launches.clear();
+            for (void *d : P->dev_allocs) cudaFree(d);
+            P->dev_allocs.clear();
+            P->mixed_infos.clear();
+            B.cache.clear();
+            P->work[0] = P->work[1] = nullptr;
+            P->work_bytes = 0;
+        };
         ok = P->c2r ? build_c2r(B) : build_fast(B);  // (c2r: power-of-two, unit-stride layouts; anything else below)
+        if (!ok) {
+            discard();
+            if (B.err != FFTB200_SUCCESS) return B.err;
+            ok = build_mixed(B);  // complex, axes of the form 2^a 3^b 5^c 7^d that fit one shared-memory tile
+        }
         if (!ok) {
             // discard partial fast plan
             P->launches.clear();

@@ -183,6 +183,14 @@ static int run_launches(Plan *P, const void *in, void *out, int inverse) {
             tp.out = (char *)dst + (size_t)ln.out_off * elt;
             tp.inverse = ln.dir_override ? (ln.dir_override == 2) : inverse;
             ce = launch_tile(ln.ki, ln.grid, P->stream, tp);
+        } else if (ln.kind == Launch::MIXED) {
+            TileParams tp = ln.tp;
+            const size_t elt = P->prec ? 16 : 8;
+            tp.in = (const char *)src + (size_t)ln.in_off * elt;
+            tp.out = (char *)dst + (size_t)ln.out_off * elt;
+            tp.inverse = inverse;
+            reinterpret_cast<MixedKernelFn>(ln.ki->fn)<<<ln.grid, ln.ki->threads, ln.ki->smem_bytes, P->stream>>>(tp, ln.mixed);
+            ce = report(cudaGetLastError(), ln.ki, ln.grid);
         } else {
             ce = P->prec ? launch_generic<double>(ln, src, dst, inverse, P->stream)
                          : launch_generic<float>(ln, src, dst, inverse, P->stream);

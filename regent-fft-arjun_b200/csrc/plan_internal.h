@@ -12,6 +12,7 @@
 
 #include "../../include/fft_b200.h"
 #include "generic_kernels.cuh"
+#include "mixed_kernel.cuh"
 #include "tile_registry.h"
 
 namespace fftb200 {
@@ -19,11 +20,14 @@ namespace fftb200 {
 enum BufSel { BUF_IN = 0, BUF_OUT = 1, BUF_WORK0 = 2, BUF_WORK1 = 3, BUF_BLU = 4 };
 
 struct Launch {
-    enum Kind { TILE, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER, BLU_PRE, BLU_MUL, BLU_POST, GEN_GATHER_HERM, GEN_SCATTER_REAL } kind = TILE;
+    enum Kind { TILE, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER, BLU_PRE, BLU_MUL, BLU_POST, GEN_GATHER_HERM, GEN_SCATTER_REAL, MIXED } kind = TILE;
     // TILE
     const TileKernelInfo *ki = nullptr;
     TileParams tp{};
     int variant = 0;
+    // MIXED (mixed_kernel.cuh): ki / tp as for TILE (ki owned by the plan), plus the radix list
+    MixedStages mixed{};
+    bool mixed_row = false;
     // generic
     GenLayout lay{};
     long long total = 0, outer = 0, inner = 0;
@@ -58,6 +62,7 @@ struct Plan {
     bool inplace_ok = false;  // in == out allowed
     std::vector<Launch> launches;
     std::vector<void *> dev_allocs;
+    std::vector<std::unique_ptr<TileKernelInfo>> mixed_infos;  // tile shapes of MIXED launches (chosen per plan)
     void *work[2] = {nullptr, nullptr};
     void *blu = nullptr;  // Bluestein convolution buffer (generic plans with a large prime factor)
     size_t blu_bytes = 0;

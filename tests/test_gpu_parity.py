@@ -840,12 +840,58 @@ def test_large_prime_lengths_use_bluestein(L, oracle):
         if kind in ("z2z", "c2c"):
             back, _ = gpu_fft(L, kind, got, shape, direction=+1)
             assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * oracle.tolerance(int(np.prod(shape)), kind == "c2c")
-    for kind, shape in [("z2z", (3, 3, 2)), ("z2z", (5,)), ("z2z", (1000,)), ("z2z", (31 * 4,))]:
+    for kind, shape in [("z2z", (11, 13)), ("z2z", (2 * 3 * 11,)), ("z2z", (31 * 4,)), ("d2z", (3, 3, 2)), ("d2z", (1000,))]:
         _, dt_in, _ = _kinds(L)[kind]
         x = oracle.synth(shape, dt_in, 995)
         got, desc = gpu_fft(L, kind, x, shape)
         assert "bluestein" not in desc and "generic stage" in desc, desc
         assert oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape)) <= oracle.tolerance(int(np.prod(shape)), False)
+
+
+def test_mixed_radix_lengths_run_one_kernel_per_axis(L, oracle):
+    """Complex transforms whose axes are products of 2, 3, 5 and 7 (the reference's own 3, 5, {3,2,2}, {3,3,2}:
+    test/fft_test.rg:143,247,328,349; FFTW's n1_3 / n1_5 / n1_7 codelets on the CPU path) run as ONE shared-memory
+    kernel per axis (mixed_kernel.cuh), power-of-two axes of such shapes on the tuned tile kernels.  Forward against
+    FFTW, backward round trip, in place, batched, both precisions."""
+    cases = [("z2z", (3,)), ("z2z", (5,)), ("z2z", (6,)), ("z2z", (7,)), ("z2z", (12,)), ("z2z", (96,)), ("z2z", (100,)),
+             ("z2z", (360,)), ("z2z", (1000,)), ("z2z", (1536,)), ("z2z", (5040,)), ("z2z", (6000,)), ("c2c", (3 * 4096,)),
+             ("z2z", (3, 2, 2)), ("z2z", (3, 3, 2)), ("z2z", (96, 96)), ("z2z", (100, 60)), ("z2z", (7, 1024)),
+             ("z2z", (1024, 9)), ("c2c", (45, 50)), ("z2z", (96, 96, 96)), ("z2z", (60, 64, 100)), ("c2c", (30, 42, 70)),
+             ("z2z", (1, 15)), ("z2z", (15, 1))]
+    for kind, shape in cases:
+        _, dt_in, _ = _kinds(L)[kind]
+        x = oracle.synth(shape, dt_in, 940 + len(shape))
+        got, desc = gpu_fft(L, kind, x, shape)
+        assert "mixed-radix" in desc and "generic" not in desc, (shape, desc)
+        tol = oracle.tolerance(int(np.prod(shape)), kind == "c2c")
+        err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape))
+        assert err <= tol, (kind, shape, err)
+        back, _ = gpu_fft(L, kind, got, shape, direction=+1)
+        assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * tol, (kind, shape)
+    # batched
+    for kind, shape, batch in [("z2z", (120,), 37), ("z2z", (12, 10), 5), ("c2c", (6, 10, 14), 3)]:
+        _, dt_in, _ = _kinds(L)[kind]
+        x = oracle.synth((batch,) + shape, dt_in, 951)
+        got, desc = gpu_fft(L, kind, x, shape, batch=batch)
+        assert "mixed-radix" in desc, desc
+        assert oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape, batch=batch)) <= oracle.tolerance(int(np.prod(shape)), kind == "c2c")
+    # in place (each pass loads its whole tile before it stores)
+    for shape in [(1000,), (96, 100), (48, 56, 60)]:
+        ftype, dt_in, _ = _kinds(L)["z2z"]
+        x = oracle.synth(shape, dt_in, 953)
+        buf = torch.from_numpy(x.copy()).cuda()
+        h = L.plan_many(len(shape), list(shape), None, 0, 0, None, 0, 0, ftype, 1)
+        L.execute(h, ftype, buf.data_ptr(), buf.data_ptr())
+        torch.cuda.synchronize()
+        L.destroy(h)
+        assert oracle.rel_l2(buf.cpu().numpy(), cpu_fft(oracle, "z2z", x, shape)) <= oracle.tolerance(int(np.prod(shape)), False)
+    # lengths past one shared-memory tile, or with other primes, stay on the generic path
+    for shape in [(4 * 5 ** 5,), (11 * 8,)]:
+        _, dt_in, _ = _kinds(L)["z2z"]
+        x = oracle.synth(shape, dt_in, 955)
+        got, desc = gpu_fft(L, "z2z", x, shape)
+        assert "mixed-radix" not in desc, desc
+        assert oracle.rel_l2(got, cpu_fft(oracle, "z2z", x, shape)) <= oracle.tolerance(int(np.prod(shape)), False)
 
 
 def test_inplace_r2c_padded_layout(L, oracle):
