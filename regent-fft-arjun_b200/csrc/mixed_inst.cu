@@ -1,12 +1,13 @@
-// mixed_inst.cu — the instantiations of the mixed-radix shared-memory kernel (mixed_kernel.cuh)
+// mixed_inst.cu — lookup of the mixed-radix shared-memory kernels (mixed_kernel.cuh); the instantiations live in
+// mixed_inst_f32_r*.cu / mixed_inst_f64_r*.cu (one translation unit per precision and largest radix)
 #include "mixed_kernel.cuh"
 
 namespace fftb200 {
 
 template <typename T> static MixedKernelFn pick(bool rowmap, int maxr) {
-    if (maxr <= 8) return rowmap ? fft_mixed_kernel<T, true, 8> : fft_mixed_kernel<T, false, 8>;
-    if (maxr <= 10) return rowmap ? fft_mixed_kernel<T, true, 10> : fft_mixed_kernel<T, false, 10>;
-    return rowmap ? fft_mixed_kernel<T, true, 16> : fft_mixed_kernel<T, false, 16>;
+    if (maxr <= 8) return mixed_kernel_inst<T, 8>(rowmap);
+    if (maxr <= 10) return mixed_kernel_inst<T, 10>(rowmap);
+    return mixed_kernel_inst<T, 16>(rowmap);
 }
 
 MixedKernelFn mixed_kernel(int prec, bool rowmap, int maxr) { return prec ? pick<double>(rowmap, maxr) : pick<float>(rowmap, maxr); }

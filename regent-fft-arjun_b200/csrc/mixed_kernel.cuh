@@ -64,26 +64,40 @@ __device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStag
             C a[P];
             if (SRC_G) {
                 const int wi = min(i0 + w, p.n_inner - 1);  // (a ragged last tile re-reads its last valid line; never stored)
-                const C *g = gin + (long long)wi * p.in_is + (long long)j * p.in_ls;
-                const long long st = (long long)Lp * p.in_ls;
+                if (ROWMAP) {  // unit element stride: 32-bit offsets from the line's base
+                    const C *g = gin + (long long)wi * p.in_is + j;
 #pragma unroll
-                for (int t = 0; t < P; ++t) a[t] = conj_if(__ldg(g + t * st), cmask);
+                    for (int t = 0; t < P; ++t) a[t] = conj_if(__ldg(g + (unsigned)(t * Lp)), cmask);
+                } else {
+                    // (the plan guarantees (L - 1) * in_ls < 2^32: 32-bit offsets from the line's base)
+                    const C *g = gin + wi;
+                    const unsigned ls = (unsigned)p.in_ls;
+#pragma unroll
+                    for (int t = 0; t < P; ++t) a[t] = conj_if(__ldg(g + (unsigned)(j + t * Lp) * ls), cmask);
+                }
             } else {
                 const C *s = ssrc + w * s_line + j * s_elem;
 #pragma unroll
                 for (int t = 0; t < P; ++t) a[t] = s[t * Lp * s_elem];
             }
             if (Ns > 1) {
+                const C *twk = tws + k;
 #pragma unroll
-                for (int t = 1; t < P; ++t) a[t] = cmul(a[t], __ldg(tws + (t - 1) * Ns + k));
+                for (int t = 1; t < P; ++t) a[t] = cmul(a[t], __ldg(twk + (unsigned)((t - 1) * Ns)));
             }
             Dft<T, P>::run(a);
             if (DST_G) {
                 if (i0 + w < p.n_inner) {
-                    C *g = gout + (long long)(i0 + w) * p.out_is + (long long)ob * p.out_ls;
-                    const long long st = (long long)Ns * p.out_ls;
+                    if (ROWMAP) {
+                        C *g = gout + (long long)(i0 + w) * p.out_is + ob;
 #pragma unroll
-                    for (int t = 0; t < P; ++t) g[t * st] = conj_if(a[t], cmask);
+                        for (int t = 0; t < P; ++t) g[(unsigned)(t * Ns)] = conj_if(a[t], cmask);
+                    } else {
+                        C *g = gout + (i0 + w);
+                        const unsigned ls = (unsigned)p.out_ls;
+#pragma unroll
+                        for (int t = 0; t < P; ++t) g[(unsigned)(ob + t * Ns) * ls] = conj_if(a[t], cmask);
+                    }
                 }
             } else {
                 C *d = sdst + w * s_line + ob * s_elem;
@@ -137,6 +151,27 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
             default: break;
         }
 #undef FFTB200_MIXED_CASE
+        if (first && p.prefetch_tiles > 0) {
+            // L2 prefetch of the tile that will run next in this CTA slot (this tile's own loads have been consumed): the
+            // next CTA's first stage then waits for L2, not for HBM
+            const int ft = tile + p.prefetch_tiles;
+            if (ft < p.n_tiles) {
+                const int fo = fast_div(ft, p.div_tpo_m, p.div_tpo_s);
+                const int fi0 = (ft - fo * p.tiles_per_outer) * W;
+                const int fo1 = fast_div(fo, p.div_o2_m, p.div_o2_s), fo2 = fo - fo1 * p.n_o2;
+                if (fi0 + W <= p.n_inner) {  // whole tiles only: never touch addresses past the array
+                    const C *fin = reinterpret_cast<const C *>(p.in) + fo1 * p.in_os1 + fo2 * p.in_os2 + (long long)fi0 * p.in_is;
+                    const int n_run = ROWMAP ? W : L;                                   // contiguous runs of the tile
+                    const int ch_run = ((ROWMAP ? L : W) * (int)sizeof(C) + 127) / 128;  // 128-byte chunks per run
+                    const long long run_stride = ROWMAP ? p.in_is : p.in_ls;
+                    for (int ch = (int)threadIdx.x; ch < n_run * ch_run; ch += (int)blockDim.x) {
+                        const int r = ch / ch_run, cc = ch - r * ch_run;
+                        const char *a = reinterpret_cast<const char *>(fin + (long long)r * run_stride) + cc * 128;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                    }
+                }
+            }
+        }
         Ns *= P;
         if (!last) __syncthreads();
         // stage s wrote dst; the next one reads it and writes the other buffer
@@ -148,7 +183,10 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
 // host side: the instantiations (precision x mapping x largest radix compiled in: 8, 10 or 16 - the register count follows
 // the largest in-register DFT); radices the kernel has code for
 typedef void (*MixedKernelFn)(const TileParams, const MixedStages);
+// (holding the register allocation to 80 or 64 with a minimum-blocks launch bound was measured and is not a gain:
+// 384^3 fp64 1.62 -> 1.72 ms, 1536^2 0.26 -> 0.34 ms; 1000-point batches unchanged)
 MixedKernelFn mixed_kernel(int prec, bool rowmap, int maxr);
+template <typename T, int MAXR> MixedKernelFn mixed_kernel_inst(bool rowmap);
 constexpr int MIXED_RADICES[] = {16, 15, 14, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
 
 }  // namespace fftb200

@@ -522,7 +522,8 @@ static const size_t MIXED_SMEM_MAX = 200u << 10;
 
 static int mixed_max_radix(int prec) {
     // largest in-register DFT: the register count of the kernel follows it (fp64: radix 16 needs 138 registers)
-    const int dflt = prec ? 10 : 16;
+    const int dflt = 16;
+    (void)prec;
     const int v = env_int_or("FFTB200_MIXED_MAXR", dflt);
     return v <= 8 ? 8 : (v <= 10 ? 10 : 16);
 }
@@ -541,6 +542,10 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     const int maxr = mixed_max_radix(P->prec);
     const std::vector<int> rad = mixed_radices(L, maxr);
     if (rad.empty() || (int)rad.size() > MIXED_MAX_STAGES) return false;
+    // the kernel addresses a line with 32-bit element offsets from its base
+    if (in_ls < 0 || out_ls < 0 || (unsigned long long)(L - 1) * (unsigned long long)in_ls >= (1ull << 32) ||
+        (unsigned long long)(L - 1) * (unsigned long long)out_ls >= (1ull << 32))
+        return false;
     MixedStages ms{};
     ms.n = (int)rad.size();
     ms.L = L;
@@ -548,26 +553,38 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     const size_t budget = (size_t)env_int_or("FFTB200_MIXED_TILE_KB", 16) << 10;  // one shared-memory buffer
     const int nbuf = ms.n >= 3 ? 2 : (ms.n == 2 ? 1 : 0);  // exchanges between stages: ping-pong from three stages on
     int W, threads;
+    long long lp_sum = 0;
+    int lp_max = 0;
+    for (int r : rad) { lp_sum += L / r; lp_max = std::max(lp_max, L / r); }
+    // Thread layout: `c` threads share the butterflies of one line position set (stage s has L / r_s butterflies per
+    // line).  Scored by the butterfly slots that do useful work among the threads resident on an SM, estimated with
+    // 512 threads per SM (the kernels need about 128 registers) and 220 KiB of shared memory.
+    auto score = [&](int c, int useful_threads, int block_threads, size_t smem_bytes) {
+        long long cost = 0;
+        for (int r : rad) cost += (long long)((L / r + c - 1) / c) * c;
+        const double eff = (double)lp_sum / (double)cost;
+        const long long by_smem = smem_bytes ? (long long)((220u << 10) / smem_bytes) : 32;
+        const long long ctas = std::max<long long>(1, std::min<long long>({32, by_smem, 512 / block_threads}));
+        return eff * (double)(ctas * useful_threads);
+    };
     if (row) {
-        // threads along a line: the count that wastes the fewest thread slots over the stages (stage s has L / r_s
-        // butterflies per line); the rest of the CTA takes further lines
-        int lp_max = 0;
-        for (int r : rad) lp_max = std::max(lp_max, L / r);
-        const int hi = std::min(lp_max, MIXED_MAX_THREADS), lo = std::min(hi, 32);
-        long long best_cost = -1;
-        int tl = hi;
-        for (int c = lo; c <= hi; ++c) {
-            long long cost = 0;
-            for (int r : rad) cost += (long long)((L / r + c - 1) / c) * c;
-            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; tl = c; }
-        }
         ms.pitch = L | 1;  // odd: threads of one warp that sit on different lines hit different banks
-        int nslow = (int)std::min<long long>(std::max(1, MIXED_MAX_THREADS / tl), lines0);
-        const size_t line_bytes = (size_t)ms.pitch * ce;
-        int rounds = (int)std::max<size_t>(1, budget / (line_bytes * nslow));
-        while (nslow > 1 && (size_t)std::max(1, nbuf) * nslow * line_bytes > MIXED_SMEM_MAX) --nslow;
+        const size_t line_bytes = (size_t)ms.pitch * ce * std::max(1, nbuf);
+        if (line_bytes > MIXED_SMEM_MAX) return false;
+        const int hi = std::min(lp_max, MIXED_MAX_THREADS), lo = std::min(hi, 8);
+        double best = -1;
+        int tl = hi, nslow = 1;
+        for (int c = lo; c <= hi; ++c) {
+            long long ns = std::min<long long>(std::max(1, MIXED_MAX_THREADS / c), lines0);
+            ns = std::min<long long>(ns, std::max<size_t>(1, (64u << 10) / line_bytes));
+            const int bt = (int)((c * ns + 31) / 32 * 32);
+            const double sc = score(c, (int)(c * ns), bt, nbuf ? line_bytes * ns : 0);
+            if (sc >= best) { best = sc; tl = c; nslow = (int)ns; }
+        }
+        // small tiles: several rounds of nslow lines per CTA, up to the tile budget
+        int rounds = (int)std::max<size_t>(1, budget / ((size_t)ms.pitch * ce * nslow));
         rounds = (int)std::min<long long>(rounds, std::max<long long>(1, lines0 / nslow));
-        while (rounds > 1 && (size_t)std::max(1, nbuf) * nslow * rounds * line_bytes > MIXED_SMEM_MAX) --rounds;
+        while (rounds > 1 && line_bytes * nslow * rounds > MIXED_SMEM_MAX) --rounds;
         W = nslow * rounds;
         ms.nfast = tl;
         ms.nslow = nslow;
@@ -577,12 +594,14 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
         while (W > 1 && (size_t)std::max(1, nbuf) * L * W * ce > MIXED_SMEM_MAX) W /= 2;
         ms.nfast = W;
         ms.pitch = 0;
-        // enough butterfly slots for the widest stage, in whole warps
-        int lp_max = 0;
-        for (int r : rad) lp_max = std::max(lp_max, L / r);
-        int nslow = 1;
-        while (nslow * 2 * W <= MIXED_MAX_THREADS && nslow < lp_max) nslow *= 2;
-        while (nslow * W < 32) nslow *= 2;
+        const size_t tile_bytes = (size_t)nbuf * L * W * ce;
+        const int unit = std::max(1, 32 / W);  // whole warps
+        double best = -1;
+        int nslow = unit;
+        for (int c = unit; c * W <= MIXED_MAX_THREADS && c < lp_max + unit; c += unit) {
+            const double sc = score(c, c * W, c * W, tile_bytes);
+            if (sc >= best) { best = sc; nslow = c; }
+        }
         ms.nslow = nslow;
         threads = nslow * W;
     }
@@ -640,6 +659,13 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     ln.mixed_row = row;
     ln.tp.tw = dtw;
     ln.tp.prefetch_tiles = 0;
+    if (env_int_or("FFTB200_MIXED_PREFETCH", 1) != 0) {
+        // distance = CTAs resident on the GPU: the tile this CTA's slot runs next
+        int sms = 148, per_sm = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, P->device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)ki->fn, threads, smem) != cudaSuccess) cudaGetLastError();
+        ln.tp.prefetch_tiles = sms * std::max(1, per_sm);
+    }
     std::string radices;
     for (int i = 0; i < ms.n; ++i) radices += (i ? "x" : "") + std::to_string((int)ms.r[i]);
     char buf[256];

@@ -51,13 +51,13 @@ for prec, shape, batch in [("z2z", (96, 96, 96), 1), ("z2z", (192, 192, 192), 1)
     ms_g, n_g, _ = ours(x, y, shape, batch, ftype, False)
     variants = {}
     if os.environ.get("MIXED_PROBE_VARIANTS"):
-        for maxr in (8, 10, 16):
-            for kb in (8, 16, 32):
-                try:
-                    v_ms, _, v_desc = ours(x, y, shape, batch, ftype, True, {"FFTB200_MIXED_MAXR": maxr, "FFTB200_MIXED_TILE_KB": kb})
-                    variants[f"maxr{maxr}_kb{kb}"] = round(v_ms, 4)
-                except Exception as ex:
-                    variants[f"maxr{maxr}_kb{kb}"] = str(ex)
+        for name, env in [("maxr10", {"FFTB200_MIXED_MAXR": 10}), ("maxr8", {"FFTB200_MIXED_MAXR": 8}),
+                          ("kb32", {"FFTB200_MIXED_TILE_KB": 32}), ("kb64", {"FFTB200_MIXED_TILE_KB": 64})]:
+            try:
+                v_ms, _, v_desc = ours(x, y, shape, batch, ftype, True, env)
+                variants[name] = round(v_ms, 4)
+            except Exception as ex:
+                variants[name] = str(ex)
     ref = torch.fft.fftn(x, dim=dims)
     ms_c = timed(lambda: torch.fft.fftn(x, dim=dims))
     rel = lambda a: float((torch.linalg.vector_norm((a - ref).to(torch.complex128)) / torch.linalg.vector_norm(ref.to(torch.complex128))).item())
