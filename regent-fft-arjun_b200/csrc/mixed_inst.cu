@@ -4,12 +4,15 @@
 
 namespace fftb200 {
 
-template <typename T> static MixedKernelFn pick(bool rowmap, int maxr) {
-    if (maxr <= 8) return mixed_kernel_inst<T, 8>(rowmap);
-    if (maxr <= 10) return mixed_kernel_inst<T, 10>(rowmap);
-    return mixed_kernel_inst<T, 16>(rowmap);
+template <typename T> static MixedKernelFn pick(bool rowmap, int maxr, int io) {
+    if (maxr <= 8) return mixed_kernel_inst<T, 8>(rowmap, io);
+    if (maxr <= 10) return mixed_kernel_inst<T, 10>(rowmap, io);
+    return mixed_kernel_inst<T, 16>(rowmap, io);
 }
 
-MixedKernelFn mixed_kernel(int prec, bool rowmap, int maxr) { return prec ? pick<double>(rowmap, maxr) : pick<float>(rowmap, maxr); }
+MixedKernelFn mixed_kernel(int prec, bool rowmap, int maxr, int io) {
+    if (io != MIXED_C2C && !rowmap) return nullptr;
+    return prec ? pick<double>(rowmap, maxr, io) : pick<float>(rowmap, maxr, io);
+}
 
 }  // namespace fftb200

@@ -2,7 +2,10 @@
 #include "mixed_kernel.cuh"
 
 namespace fftb200 {
-template <> MixedKernelFn mixed_kernel_inst<double, 8>(bool rowmap) {
-    return rowmap ? fft_mixed_kernel<double, true, 8> : fft_mixed_kernel<double, false, 8>;
+template <> MixedKernelFn mixed_kernel_inst<double, 8>(bool rowmap, int io) {
+    if (!rowmap) return fft_mixed_kernel<double, false, 8, MIXED_C2C>;
+    if (io == MIXED_R2C) return fft_mixed_kernel<double, true, 8, MIXED_R2C>;
+    if (io == MIXED_C2R) return fft_mixed_kernel<double, true, 8, MIXED_C2R>;
+    return fft_mixed_kernel<double, true, 8, MIXED_C2C>;
 }
 }  // namespace fftb200

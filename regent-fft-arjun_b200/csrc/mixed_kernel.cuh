@@ -44,9 +44,15 @@ struct MixedStages {
 // one stores straight to it (both coalesced: for a fixed t consecutive butterflies touch consecutive elements), so only
 // the exchanges between stages go through shared memory.
 //   SRC_G / DST_G: source / destination is global memory (strides in TileParams) instead of shared memory
-template <typename T, int P, bool ROWMAP, bool SRC_G, bool DST_G>
-__device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStages &ms, const cplx<T> *__restrict__ gin,
-                                            cplx<T> *__restrict__ gout, const cplx<T> *__restrict__ ssrc,
+//   IO (contiguous axis only): MIXED_C2C complex lines in and out;
+//       MIXED_R2C  lines of L reals in (taken as complex with zero imaginary part), the first L/2+1 outputs stored;
+//       MIXED_C2R  lines of L/2+1 complex in, completed to the full Hermitian line while loading, the backward transform's
+//                  real part stored as L reals (strides of the real side are in real elements)
+enum { MIXED_C2C = 0, MIXED_R2C = 1, MIXED_C2R = 2 };
+
+template <typename T, int P, bool ROWMAP, bool SRC_G, bool DST_G, int IO>
+__device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStages &ms, const void *__restrict__ gin,
+                                            void *__restrict__ gout, const cplx<T> *__restrict__ ssrc,
                                             cplx<T> *__restrict__ sdst, const cplx<T> *__restrict__ tws, const int Ns,
                                             const unsigned nm, const unsigned nsh, const int i0, const int f, const int sl,
                                             const unsigned cmask) {
@@ -64,13 +70,28 @@ __device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStag
             C a[P];
             if (SRC_G) {
                 const int wi = min(i0 + w, p.n_inner - 1);  // (a ragged last tile re-reads its last valid line; never stored)
-                if (ROWMAP) {  // unit element stride: 32-bit offsets from the line's base
-                    const C *g = gin + (long long)wi * p.in_is + j;
+                if (IO == MIXED_R2C) {
+                    const T *g = reinterpret_cast<const T *>(gin) + (long long)wi * p.in_is + j;
+#pragma unroll
+                    for (int t = 0; t < P; ++t) a[t] = mk<T>(__ldg(g + (unsigned)(t * Lp)), (T)0);
+                } else if (IO == MIXED_C2R) {
+                    // conj(X_full[l]): X_full[l] = X[l] for l <= L/2, conj(X[L - l]) above (conj in, conj out = backward)
+                    const C *g = reinterpret_cast<const C *>(gin) + (long long)wi * p.in_is;
+                    const int half = ms.L >> 1;
+#pragma unroll
+                    for (int t = 0; t < P; ++t) {
+                        const int l = j + t * Lp;
+                        const bool low = l <= half;
+                        const C v = __ldg(g + (unsigned)(low ? l : ms.L - l));
+                        a[t] = low ? mk<T>(v.x, -v.y) : v;
+                    }
+                } else if (ROWMAP) {  // unit element stride: 32-bit offsets from the line's base
+                    const C *g = reinterpret_cast<const C *>(gin) + (long long)wi * p.in_is + j;
 #pragma unroll
                     for (int t = 0; t < P; ++t) a[t] = conj_if(__ldg(g + (unsigned)(t * Lp)), cmask);
                 } else {
                     // (the plan guarantees (L - 1) * in_ls < 2^32: 32-bit offsets from the line's base)
-                    const C *g = gin + wi;
+                    const C *g = reinterpret_cast<const C *>(gin) + wi;
                     const unsigned ls = (unsigned)p.in_ls;
 #pragma unroll
                     for (int t = 0; t < P; ++t) a[t] = conj_if(__ldg(g + (unsigned)(j + t * Lp) * ls), cmask);
@@ -88,12 +109,22 @@ __device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStag
             Dft<T, P>::run(a);
             if (DST_G) {
                 if (i0 + w < p.n_inner) {
-                    if (ROWMAP) {
-                        C *g = gout + (long long)(i0 + w) * p.out_is + ob;
+                    if (IO == MIXED_R2C) {
+                        C *g = reinterpret_cast<C *>(gout) + (long long)(i0 + w) * p.out_is;
+                        const int half = ms.L >> 1;
+#pragma unroll
+                        for (int t = 0; t < P; ++t)
+                            if (ob + t * Ns <= half) g[(unsigned)(ob + t * Ns)] = a[t];
+                    } else if (IO == MIXED_C2R) {
+                        T *g = reinterpret_cast<T *>(gout) + (long long)(i0 + w) * p.out_is + ob;
+#pragma unroll
+                        for (int t = 0; t < P; ++t) g[(unsigned)(t * Ns)] = a[t].x;
+                    } else if (ROWMAP) {
+                        C *g = reinterpret_cast<C *>(gout) + (long long)(i0 + w) * p.out_is + ob;
 #pragma unroll
                         for (int t = 0; t < P; ++t) g[(unsigned)(t * Ns)] = conj_if(a[t], cmask);
                     } else {
-                        C *g = gout + (i0 + w);
+                        C *g = reinterpret_cast<C *>(gout) + (i0 + w);
                         const unsigned ls = (unsigned)p.out_ls;
 #pragma unroll
                         for (int t = 0; t < P; ++t) g[(unsigned)(ob + t * Ns) * ls] = conj_if(a[t], cmask);
@@ -108,7 +139,7 @@ __device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStag
     }
 }
 
-template <typename T, bool ROWMAP, int MAXR>
+template <typename T, bool ROWMAP, int MAXR, int IO>
 __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const TileParams p, const MixedStages ms) {
     using C = cplx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -120,10 +151,14 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
     const int o = fast_div(tile, p.div_tpo_m, p.div_tpo_s);
     const int i0 = (tile - o * p.tiles_per_outer) * W;
     const int o1 = fast_div(o, p.div_o2_m, p.div_o2_s), o2 = o - o1 * p.n_o2;
-    const C *__restrict__ gin = reinterpret_cast<const C *>(p.in) + o1 * p.in_os1 + o2 * p.in_os2;
-    C *__restrict__ gout = reinterpret_cast<C *>(p.out) + o1 * p.out_os1 + o2 * p.out_os2;
+    static_assert(IO == MIXED_C2C || ROWMAP, "real transforms: contiguous axis only");
+    // (the real side of a real transform is addressed in real elements)
+    const void *__restrict__ gin = reinterpret_cast<const char *>(p.in) +
+                                   (o1 * p.in_os1 + o2 * p.in_os2) * (long long)(IO == MIXED_R2C ? sizeof(T) : sizeof(C));
+    void *__restrict__ gout = reinterpret_cast<char *>(p.out) +
+                              (o1 * p.out_os1 + o2 * p.out_os2) * (long long)(IO == MIXED_C2R ? sizeof(T) : sizeof(C));
     const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);
-    const unsigned cmask = p.inverse ? 0x80000000u : 0u;
+    const unsigned cmask = (IO == MIXED_C2C && p.inverse) ? 0x80000000u : 0u;
     int sl = (int)threadIdx.x / ms.nfast;
     const int f = (int)threadIdx.x - sl * ms.nfast;
     if (sl >= ms.nslow) sl = 1 << 30;  // threads past nfast * nslow (block rounded up to whole warps) only take part in the barriers
@@ -138,10 +173,10 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
 #define FFTB200_MIXED_CASE(R)                                                                                        \
     case R:                                                                                                          \
         if constexpr (R <= MAXR) {                                                                                   \
-            if (first && last) mixed_stage<T, R, ROWMAP, true, true>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);        \
-            else if (first) mixed_stage<T, R, ROWMAP, true, false>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);     \
-            else if (last) mixed_stage<T, R, ROWMAP, false, true>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);      \
-            else mixed_stage<T, R, ROWMAP, false, false>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);               \
+            if (first && last) mixed_stage<T, R, ROWMAP, true, true, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);        \
+            else if (first) mixed_stage<T, R, ROWMAP, true, false, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);     \
+            else if (last) mixed_stage<T, R, ROWMAP, false, true, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);      \
+            else mixed_stage<T, R, ROWMAP, false, false, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);               \
         }                                                                                                            \
         break;
         switch (P) {
@@ -160,13 +195,16 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
                 const int fi0 = (ft - fo * p.tiles_per_outer) * W;
                 const int fo1 = fast_div(fo, p.div_o2_m, p.div_o2_s), fo2 = fo - fo1 * p.n_o2;
                 if (fi0 + W <= p.n_inner) {  // whole tiles only: never touch addresses past the array
-                    const C *fin = reinterpret_cast<const C *>(p.in) + fo1 * p.in_os1 + fo2 * p.in_os2 + (long long)fi0 * p.in_is;
+                    constexpr int IN_ELT = IO == MIXED_R2C ? (int)sizeof(T) : (int)sizeof(C);
+                    const char *fin = reinterpret_cast<const char *>(p.in) +
+                                      (fo1 * p.in_os1 + fo2 * p.in_os2 + (long long)fi0 * p.in_is) * IN_ELT;
                     const int n_run = ROWMAP ? W : L;                                   // contiguous runs of the tile
-                    const int ch_run = ((ROWMAP ? L : W) * (int)sizeof(C) + 127) / 128;  // 128-byte chunks per run
+                    const int run_elems = ROWMAP ? (IO == MIXED_C2R ? L / 2 + 1 : L) : W;
+                    const int ch_run = (run_elems * IN_ELT + 127) / 128;                 // 128-byte chunks per run
                     const long long run_stride = ROWMAP ? p.in_is : p.in_ls;
                     for (int ch = (int)threadIdx.x; ch < n_run * ch_run; ch += (int)blockDim.x) {
                         const int r = ch / ch_run, cc = ch - r * ch_run;
-                        const char *a = reinterpret_cast<const char *>(fin + (long long)r * run_stride) + cc * 128;
+                        const char *a = fin + (long long)r * run_stride * IN_ELT + cc * 128;
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
                     }
                 }
@@ -185,8 +223,8 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
 typedef void (*MixedKernelFn)(const TileParams, const MixedStages);
 // (holding the register allocation to 80 or 64 with a minimum-blocks launch bound was measured and is not a gain:
 // 384^3 fp64 1.62 -> 1.72 ms, 1536^2 0.26 -> 0.34 ms; 1000-point batches unchanged)
-MixedKernelFn mixed_kernel(int prec, bool rowmap, int maxr);
-template <typename T, int MAXR> MixedKernelFn mixed_kernel_inst(bool rowmap);
+MixedKernelFn mixed_kernel(int prec, bool rowmap, int maxr, int io);
+template <typename T, int MAXR> MixedKernelFn mixed_kernel_inst(bool rowmap, int io);
 constexpr int MIXED_RADICES[] = {16, 15, 14, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
 
 }  // namespace fftb200

@@ -535,9 +535,11 @@ static bool mixed_axis_ok(long long L, int prec) {
     return !r.empty() && (int)r.size() <= MIXED_MAX_STAGES && nbuf * (size_t)(L + 1) * (prec ? 16 : 8) <= MIXED_SMEM_MAX;
 }
 
+// io: MIXED_C2C, or (contiguous axis only) MIXED_R2C / MIXED_C2R with the real side's strides in real elements
 static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long long out_ls, std::vector<Level> lv, int src,
-                           int dst, const char *what) {
+                           int dst, const char *what, int io = MIXED_C2C) {
     Plan *P = B.P;
+    if (io != MIXED_C2C && !row) return false;
     const size_t ce = P->prec ? 16 : 8;
     const int maxr = mixed_max_radix(P->prec);
     const std::vector<int> rad = mixed_radices(L, maxr);
@@ -643,7 +645,7 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     int kmax = 0;
     for (int r : rad) kmax = std::max(kmax, r);
     std::unique_ptr<TileKernelInfo> ki(new TileKernelInfo);
-    ki->fn = reinterpret_cast<void (*)(const TileParams)>(mixed_kernel(P->prec, row, kmax));  // (launched with its own signature)
+    ki->fn = reinterpret_cast<void (*)(const TileParams)>(mixed_kernel(P->prec, row, kmax, io));  // (launched with its own signature)
     ki->L = L;
     ki->R = L;  // no per-stage tile tables: add_tile_pass_with leaves tp.tw alone
     ki->W = W;
@@ -657,6 +659,10 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     ln.kind = Launch::MIXED;
     ln.mixed = ms;
     ln.mixed_row = row;
+    if (io != MIXED_C2C) {
+        const unsigned long long lines = ln.algo_bytes / ((unsigned long long)L * ce * 2ull);
+        ln.algo_bytes = lines * ((unsigned long long)L * (ce / 2) + (unsigned long long)(L / 2 + 1) * ce);
+    }
     ln.tp.tw = dtw;
     ln.tp.prefetch_tiles = 0;
     if (env_int_or("FFTB200_MIXED_PREFETCH", 1) != 0) {
@@ -670,7 +676,8 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     for (int i = 0; i < ms.n; ++i) radices += (i ? "x" : "") + std::to_string((int)ms.r[i]);
     char buf[256];
     snprintf(buf, sizeof buf, "mixed-radix %s %s L=%d (%s) W=%d threads=%d (%d along %s) smem=%d tiles=%u (%s)",
-             row ? "row" : "col", P->prec ? "fp64" : "fp32", L, radices.c_str(), W, threads, ms.nfast,
+             io == MIXED_R2C ? "r2c-row" : (io == MIXED_C2R ? "c2r-row" : (row ? "row" : "col")), P->prec ? "fp64" : "fp32", L,
+             radices.c_str(), W, threads, ms.nfast,
              row ? "a line" : "the lines", (int)smem, ln.grid, what);
     ln.desc = buf;
     P->mixed_infos.push_back(std::move(ki));
@@ -681,9 +688,9 @@ static bool build_mixed(Builder &B) {
     Plan *P = B.P;
     const int rank = P->rank, last = rank - 1;
     const long long *n = P->n;
-    if (P->real || P->c2r) return false;
     if (env_int_or("FFTB200_MIXED", 1) == 0) return false;
     if (P->in_stride[rank] != 1 || P->out_stride[rank] != 1) return false;
+    const bool real = P->real, c2r = P->c2r;
     const int maxL = max_tile_length(P->prec);
     long long total = 1;
     for (int d = 0; d < rank; ++d) {
@@ -692,30 +699,98 @@ static bool build_mixed(Builder &B) {
         if (!(is_pow2(n[d]) && n[d] <= maxL) && !mixed_axis_ok(n[d], P->prec)) return false;
     }
     if (total == 1) return false;
+    if ((real || c2r) && n[last] < 2) return false;
+    const long long nc = n[last] / 2 + 1;
+    // one pass along `axis`: the tuned power-of-two tile kernel when there is one, else the mixed-radix kernel
+    auto axis_pass = [&](bool row, int L, long long in_ls, long long out_ls, const std::vector<Level> &lv, int src, int dst,
+                         const char *what) {
+        if (is_pow2(L) && find_tile_kernel(P->prec, row ? V_RR : V_CC, L))
+            return add_tile_pass(B, row ? V_RR : V_CC, L, in_ls, out_ls, lv, src, dst, 0, what);
+        return add_mixed_pass(B, row, L, in_ls, out_ls, lv, src, dst, what);
+    };
+
+    if (c2r) {
+        // backward passes over the n_last/2+1 columns through a work buffer (the input survives), then the last axis:
+        // half-spectrum lines -> real lines
+        long long outer_axes = 1;
+        for (int d = 0; d < last; ++d) outer_axes *= n[d];
+        const size_t ce = P->prec ? 16 : 8;
+        int cur = BUF_IN;
+        long long cs[4];  // strides of the current complex array, [batch, d0.., d_last]
+        for (int d = 0; d <= rank; ++d) cs[d] = P->in_stride[d];
+        if (outer_axes > 1) {
+            long long ws[4];  // dense work layout [batch][n0]..[nc]
+            ws[rank] = 1;
+            for (int d = rank - 1; d >= 0; --d) ws[d] = ws[d + 1] * (d == last ? nc : n[d]);
+            P->work_bytes = (size_t)(ws[0] * P->batch) * ce;
+            P->work[0] = B.alloc(P->work_bytes);
+            if (!P->work[0]) return false;
+            for (int axis = last - 1; axis >= 0; --axis) {
+                if (n[axis] == 1) continue;
+                std::vector<Level> lv;
+                for (int d = rank - 1; d >= 0; --d) {
+                    if (d == axis) continue;
+                    lv.push_back({d == last ? nc : n[d], cs[d + 1], ws[d + 1]});
+                }
+                lv.push_back({(long long)P->batch, cs[0], ws[0]});
+                if (!axis_pass(false, (int)n[axis], cs[axis + 1], ws[axis + 1], lv, cur, BUF_WORK0, "strided axis (backward)"))
+                    return false;
+                cur = BUF_WORK0;
+                for (int d = 0; d <= rank; ++d) cs[d] = ws[d];
+            }
+        }
+        bool even_out = true;
+        for (int d = 0; d < rank; ++d) even_out = even_out && !(P->out_stride[d] & 1);
+        const bool tile_last = is_pow2(n[last]) && n[last] >= 4 && even_out && find_tile_kernel(P->prec, V_RR_C2R, (int)(n[last] / 2));
+        std::vector<Level> lv;
+        const long long div = tile_last ? 2 : 1;  // (the tile kernel addresses the reals as complex pairs)
+        for (int d = last - 1; d >= 0; --d) lv.push_back({n[d], cs[d + 1], P->out_stride[d + 1] / div});
+        lv.push_back({(long long)P->batch, cs[0], P->out_stride[0] / div});
+        if (tile_last) {
+            if (!add_tile_pass(B, V_RR_C2R, (int)(n[last] / 2), 1, 1, lv, cur, BUF_OUT, 0, "axis c2r")) return false;
+            P->inplace_ok = false;
+        } else {
+            if (!add_mixed_pass(B, true, (int)n[last], 1, 1, lv, cur, BUF_OUT, "axis c2r", MIXED_C2R)) return false;
+            // in place: through the work buffer the input is consumed before the output is written; a direct pass is
+            // safe when every CTA's lines occupy the same bytes on both sides (it loads its tile before it stores)
+            P->inplace_ok = outer_axes > 1 || P->batch == 1 || P->out_stride[0] == 2 * P->in_stride[0];
+        }
+        return true;
+    }
+
+    long long nout[3];
+    for (int d = 0; d < rank; ++d) nout[d] = n[d];
+    if (real) nout[last] = nc;
     auto levels_for = [&](int axis, bool first_pass) {
         std::vector<Level> lv;
         for (int d = rank - 1; d >= 0; --d) {
             if (d == axis) continue;
-            lv.push_back({n[d], first_pass ? P->in_stride[d + 1] : P->out_stride[d + 1], P->out_stride[d + 1]});
+            lv.push_back({first_pass ? n[d] : nout[d], first_pass ? P->in_stride[d + 1] : P->out_stride[d + 1], P->out_stride[d + 1]});
         }
         lv.push_back({P->batch, first_pass ? P->in_stride[0] : P->out_stride[0], P->out_stride[0]});
         return lv;
     };
     bool first = true;
-    for (int axis = last; axis >= 0; --axis) {
+    if (real) {
+        bool even_in = true;
+        for (int d = 0; d < rank; ++d) even_in = even_in && !(P->in_stride[d] & 1);
+        std::vector<Level> lv = levels_for(last, true);
+        if (is_pow2(n[last]) && n[last] >= 4 && even_in && find_tile_kernel(P->prec, V_RR_R2C, (int)(n[last] / 2))) {
+            for (Level &l : lv) l.is /= 2;  // input addressed as packed complex pairs
+            if (!add_tile_pass(B, V_RR_R2C, (int)(n[last] / 2), 1, 1, lv, BUF_IN, BUF_OUT, 0, "axis r2c")) return false;
+        } else {
+            if (!add_mixed_pass(B, true, (int)n[last], 1, 1, lv, BUF_IN, BUF_OUT, "axis r2c", MIXED_R2C)) return false;
+        }
+        first = false;
+    }
+    for (int axis = real ? last - 1 : last; axis >= 0; --axis) {
         if (n[axis] == 1) continue;
         const bool row = axis == last;
         const long long in_ls = first ? P->in_stride[axis + 1] : P->out_stride[axis + 1];
         const long long out_ls = P->out_stride[axis + 1];
-        const int src = first ? BUF_IN : BUF_OUT;
-        bool ok;
-        if (is_pow2(n[axis]) && find_tile_kernel(P->prec, row ? V_RR : V_CC, (int)n[axis]))
-            ok = add_tile_pass(B, row ? V_RR : V_CC, (int)n[axis], in_ls, out_ls, levels_for(axis, first), src, BUF_OUT, 0,
-                               row ? "last axis" : "strided axis");
-        else
-            ok = add_mixed_pass(B, row, (int)n[axis], in_ls, out_ls, levels_for(axis, first), src, BUF_OUT,
-                                row ? "last axis" : "strided axis");
-        if (!ok) return false;
+        if (!axis_pass(row, (int)n[axis], in_ls, out_ls, levels_for(axis, first), first ? BUF_IN : BUF_OUT, BUF_OUT,
+                       row ? "last axis" : "strided axis"))
+            return false;
         first = false;
     }
     P->inplace_ok = layouts_coincide(P);
@@ -1050,11 +1125,11 @@ int create_plan(Plan **out, int rank, const long long *n, int batch, const long 
             P->work[0] = P->work[1] = nullptr;
             P->work_bytes = 0;
         };
-        ok = P->c2r ? build_c2r(B) : build_fast(B);  // (c2r: power-of-two, unit-stride layouts; anything else below)
+        ok = P->c2r ? build_c2r(B) : build_fast(B);  // (power-of-two, unit-stride layouts; anything else below)
         if (!ok) {
             discard();
             if (B.err != FFTB200_SUCCESS) return B.err;
-            ok = build_mixed(B);  // complex, axes of the form 2^a 3^b 5^c 7^d that fit one shared-memory tile
+            ok = build_mixed(B);  // axes of the form 2^a 3^b 5^c 7^d that fit one shared-memory tile
         }
         if (!ok) {
             // discard partial fast plan

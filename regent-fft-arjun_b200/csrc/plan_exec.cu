@@ -206,7 +206,11 @@ int exec_plan(Plan *P, const void *in, void *out, int direction) {
     if (direction != FFTB200_FORWARD && direction != FFTB200_INVERSE) return FFTB200_INVALID_VALUE;
     if (P->real && direction != FFTB200_FORWARD) return FFTB200_INVALID_VALUE;
     if (P->c2r && direction != FFTB200_INVERSE) return FFTB200_INVALID_VALUE;
-    if (in == out && !P->inplace_ok) return FFTB200_INVALID_VALUE;
+    if (in == out && !P->inplace_ok) {
+        // (mixed-radix plans replaced the generic path for these sizes, which worked in place for any layout: keep that)
+        if (!P->mixed_infos.empty()) return exec_fallback(P, in, out, direction);
+        return FFTB200_INVALID_VALUE;
+    }
     const bool host_in = is_host_memory(in), host_out = is_host_memory(out);
     if (!P->generic && !(host_in && host_out)) {
         const size_t a_in = P->real ? 2 * P->elt_in() : P->elt_in();

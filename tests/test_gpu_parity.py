@@ -802,10 +802,16 @@ def test_inverse_real_transforms(L, oracle):
     lib = L.lib()
     assert lib.fftb200_exec_d2z(h, Xd.data_ptr(), yd.data_ptr()) == L.INVALID_TYPE
     L.destroy(h)
-    # sizes that are not powers of two (odd last dimensions included) take the generic path: Hermitian completion of the
-    # half spectrum, backward complex stages (Bluestein for large primes), real part out
-    for i, (kind, shape) in enumerate([("z2d", (12,)), ("z2d", (12, 10)), ("c2r", (3, 5, 6)), ("z2d", (1000,)), ("z2d", (7, 33)),
-                                       ("z2d", (5, 4, 9)), ("z2d", (1021,)), ("c2r", (6, 127))]):
+    # sizes that are not powers of two (odd last dimensions included): products of 2, 3, 5, 7 run the mixed-radix kernels
+    # (Hermitian completion while loading the last axis), anything else the generic path (Hermitian completion of the
+    # half spectrum, backward complex stages - Bluestein for large primes - real part out)
+    for i, (kind, shape, tag) in enumerate([("z2d", (12,), "mixed-radix c2r-row"), ("z2d", (12, 10), "mixed-radix c2r-row"),
+                                            ("c2r", (3, 5, 6), "mixed-radix c2r-row"), ("z2d", (1000,), "mixed-radix c2r-row"),
+                                            ("z2d", (7, 33), "Hermitian"), ("z2d", (5, 4, 9), "mixed-radix c2r-row"),
+                                            ("z2d", (1021,), "Hermitian"), ("c2r", (6, 127), "Hermitian"),
+                                            ("z2d", (9, 7), "mixed-radix c2r-row"), ("z2d", (96, 100, 90), "mixed-radix c2r-row"),
+                                            ("c2r", (15, 1001), "Hermitian"), ("z2d", (6, 1024), "c2r-row"),
+                                            ("z2d", (128, 6), "mixed-radix c2r-row")]):
         single = kind == "c2r"
         rdt, cdt = (np.float32, np.complex64) if single else (np.float64, np.complex128)
         ftype = L.C2R if single else L.Z2D
@@ -819,10 +825,28 @@ def test_inverse_real_transforms(L, oracle):
         torch.cuda.synchronize()
         desc = L.describe(h)
         L.destroy(h)
-        assert "Hermitian" in desc, desc
+        assert tag in desc, (shape, desc)
         err = oracle.rel_l2(yd.cpu().numpy() / n_total, x.astype(np.float64))
         assert err <= 2 * oracle.tolerance(n_total, single), (kind, shape, err)
         assert np.array_equal(Xd.cpu().numpy(), X), "c2r input modified"
+
+
+def test_c2r_in_place_other_sizes(L, oracle):
+    """Z2D in place (half spectrum overwritten by the padded real rows) for sizes off the power-of-two path: mixed-radix
+    plans where the layouts coincide, the generic plan otherwise - the call must work either way."""
+    for shape in [(1000,), (12, 10), (6, 10, 14), (7, 33)]:
+        nl, ncol = shape[-1], shape[-1] // 2 + 1
+        x = oracle.synth(shape, np.float64, 1500 + len(shape))
+        X = np.ascontiguousarray(np.fft.rfftn(x))
+        buf = torch.from_numpy(X.copy()).cuda()
+        inembed, onembed = list(shape[:-1]) + [ncol], list(shape[:-1]) + [2 * ncol]
+        h = L.plan_many(len(shape), list(shape), inembed, 1, int(np.prod(inembed)), onembed, 1, int(np.prod(onembed)), L.Z2D, 1)
+        L.execute(h, L.Z2D, buf.data_ptr(), buf.data_ptr())
+        torch.cuda.synchronize()
+        L.destroy(h)
+        got = buf.cpu().numpy().view(np.float64).reshape(shape[:-1] + (2 * ncol,))[..., :nl]
+        n_total = int(np.prod(shape))
+        assert oracle.rel_l2(got / n_total, x) <= 2 * oracle.tolerance(n_total, False), shape
 
 
 def test_large_prime_lengths_use_bluestein(L, oracle):
@@ -840,7 +864,7 @@ def test_large_prime_lengths_use_bluestein(L, oracle):
         if kind in ("z2z", "c2c"):
             back, _ = gpu_fft(L, kind, got, shape, direction=+1)
             assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * oracle.tolerance(int(np.prod(shape)), kind == "c2c")
-    for kind, shape in [("z2z", (11, 13)), ("z2z", (2 * 3 * 11,)), ("z2z", (31 * 4,)), ("d2z", (3, 3, 2)), ("d2z", (1000,))]:
+    for kind, shape in [("z2z", (11, 13)), ("z2z", (2 * 3 * 11,)), ("z2z", (31 * 4,)), ("d2z", (3, 11, 2)), ("d2z", (1300,))]:
         _, dt_in, _ = _kinds(L)[kind]
         x = oracle.synth(shape, dt_in, 995)
         got, desc = gpu_fft(L, kind, x, shape)
@@ -868,13 +892,38 @@ def test_mixed_radix_lengths_run_one_kernel_per_axis(L, oracle):
         assert err <= tol, (kind, shape, err)
         back, _ = gpu_fft(L, kind, got, shape, direction=+1)
         assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * tol, (kind, shape)
+    # real input: the last axis reads reals and stores the first n/2+1 outputs; the other axes run over those columns
+    for kind, shape in [("d2z", (3,)), ("d2z", (6,)), ("d2z", (9,)), ("d2z", (1000,)), ("r2c", (1000,)), ("d2z", (3, 3, 2)),
+                        ("d2z", (96, 96, 96)), ("r2c", (60, 64, 100)), ("d2z", (100, 512)), ("d2z", (7, 15)), ("d2z", (45, 2))]:
+        _, dt_in, _ = _kinds(L)[kind]
+        x = oracle.synth(shape, dt_in, 960 + len(shape))
+        got, desc = gpu_fft(L, kind, x, shape)
+        assert "mixed-radix" in desc and "generic" not in desc, (shape, desc)
+        err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape))
+        assert err <= oracle.tolerance(int(np.prod(shape)), kind == "r2c"), (kind, shape, err)
+    # in-place real input, FFTW's padded layout
+    for shape in [(1000,), (30, 90), (12, 10, 18)]:
+        ftype = L.D2Z
+        nl, ncol = shape[-1], shape[-1] // 2 + 1
+        x = oracle.synth(shape, np.float64, 963)
+        pad = np.zeros(shape[:-1] + (2 * ncol,), dtype=np.float64)
+        pad[..., :nl] = x
+        buf = torch.from_numpy(pad).cuda()
+        inembed, onembed = list(shape[:-1]) + [2 * ncol], list(shape[:-1]) + [ncol]
+        h = L.plan_many(len(shape), list(shape), inembed, 1, int(np.prod(inembed)), onembed, 1, int(np.prod(onembed)), ftype, 1)
+        assert "mixed-radix" in L.describe(h)
+        L.execute(h, ftype, buf.data_ptr(), buf.data_ptr())
+        torch.cuda.synchronize()
+        L.destroy(h)
+        got = buf.cpu().numpy().view(np.complex128).reshape(shape[:-1] + (ncol,))
+        assert oracle.rel_l2(got, cpu_fft(oracle, "d2z", x, shape)) <= oracle.tolerance(int(np.prod(shape)), False), shape
     # batched
-    for kind, shape, batch in [("z2z", (120,), 37), ("z2z", (12, 10), 5), ("c2c", (6, 10, 14), 3)]:
+    for kind, shape, batch in [("z2z", (120,), 37), ("z2z", (12, 10), 5), ("c2c", (6, 10, 14), 3), ("d2z", (90,), 11), ("d2z", (6, 10), 4)]:
         _, dt_in, _ = _kinds(L)[kind]
         x = oracle.synth((batch,) + shape, dt_in, 951)
         got, desc = gpu_fft(L, kind, x, shape, batch=batch)
         assert "mixed-radix" in desc, desc
-        assert oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape, batch=batch)) <= oracle.tolerance(int(np.prod(shape)), kind == "c2c")
+        assert oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape, batch=batch)) <= oracle.tolerance(int(np.prod(shape)), kind in ("c2c", "r2c"))
     # in place (each pass loads its whole tile before it stores)
     for shape in [(1000,), (96, 100), (48, 56, 60)]:
         ftype, dt_in, _ = _kinds(L)["z2z"]
