@@ -38,13 +38,15 @@ def ours(x, y, shape, batch, ftype, mixed, env=None):
 
 for prec, shape, batch in [("z2z", (96, 96, 96), 1), ("z2z", (192, 192, 192), 1), ("z2z", (384, 384, 384), 1), ("z2z", (100, 100, 100), 1),
                            ("z2z", (360, 360), 64), ("z2z", (1000,), 16384), ("z2z", (1536, 1536), 4), ("z2z", (6000,), 2048),
-                           ("c2c", (384, 384, 384), 1), ("c2c", (1000,), 32768), ("z2z", (720, 1280), 8)]:
-    dt = torch.complex128 if prec == "z2z" else torch.complex64
-    ftype = L.Z2Z if prec == "z2z" else L.C2C
+                           ("c2c", (384, 384, 384), 1), ("c2c", (1000,), 32768), ("z2z", (720, 1280), 8),
+                           ("d2z", (384, 384, 384), 1), ("d2z", (1000,), 32768), ("r2c", (360, 360), 128), ("d2z", (1080, 1920), 4)]:
+    real = prec in ("d2z", "r2c")
+    dt = {"z2z": torch.complex128, "c2c": torch.complex64, "d2z": torch.float64, "r2c": torch.float32}[prec]
+    ftype = {"z2z": L.Z2Z, "c2c": L.C2C, "d2z": L.D2Z, "r2c": L.R2C}[prec]
     full = ((batch,) if batch > 1 else ()) + shape
     x = torch.zeros(full, dtype=dt, device="cuda")
-    torch.view_as_real(x).uniform_(-0.5, 0.5)
-    y = torch.empty_like(x)
+    (torch.view_as_real(x) if not real else x).uniform_(-0.5, 0.5)
+    y = torch.empty_like(x) if not real else torch.empty(full[:-1] + (full[-1] // 2 + 1,), dtype=torch.complex128 if prec == "d2z" else torch.complex64, device="cuda")
     dims = tuple(range(len(full) - len(shape), len(full)))
     ms_m, n_m, desc = ours(x, y, shape, batch, ftype, True)
     ym = y.clone()
@@ -58,10 +60,11 @@ for prec, shape, batch in [("z2z", (96, 96, 96), 1), ("z2z", (192, 192, 192), 1)
                 variants[name] = round(v_ms, 4)
             except Exception as ex:
                 variants[name] = str(ex)
-    ref = torch.fft.fftn(x, dim=dims)
-    ms_c = timed(lambda: torch.fft.fftn(x, dim=dims))
+    cufft = (lambda: torch.fft.rfftn(x, dim=dims)) if real else (lambda: torch.fft.fftn(x, dim=dims))
+    ref = cufft()
+    ms_c = timed(cufft)
     rel = lambda a: float((torch.linalg.vector_norm((a - ref).to(torch.complex128)) / torch.linalg.vector_norm(ref.to(torch.complex128))).item())
-    nbytes = x.numel() * x.element_size()
+    nbytes = (x.numel() * x.element_size() + y.numel() * y.element_size()) / 2  # mean of input and output array
     print(json.dumps({"kind": prec, "shape": shape, "batch": batch, "MiB": round(nbytes / 2**20, 1),
                       "mixed_ms": round(ms_m, 4), "mixed_launches": n_m, "mixed_GB/s_per_pass": round(2 * nbytes * n_m / ms_m / 1e6),
                       "generic_ms": round(ms_g, 4), "generic_launches": n_g, "cufft_ms": round(ms_c, 4),
