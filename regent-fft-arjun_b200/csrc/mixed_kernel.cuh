@@ -48,7 +48,14 @@ struct MixedStages {
 //       MIXED_R2C  lines of L reals in (taken as complex with zero imaginary part), the first L/2+1 outputs stored;
 //       MIXED_C2R  lines of L/2+1 complex in, completed to the full Hermitian line while loading, the backward transform's
 //                  real part stored as L reals (strides of the real side are in real elements)
-enum { MIXED_C2C = 0, MIXED_R2C = 1, MIXED_C2R = 2 };
+//       MIXED_R2C_HALF / MIXED_C2R_HALF  even L, rows starting on a pair of reals: the line of 2 Lh reals is taken as Lh
+//                  complex z[m] = x[2m] + i x[2m+1]; one Lh-point complex transform (ms.L = Lh) and an even/odd pass over
+//                  the pairs (k, Lh - k) in shared memory - after the last stage for R2C
+//                      X[k] = E + w B,  X[Lh-k] = conj(E - w B),  E = (Z[k] + conj Z[Lh-k]) / 2,  B = -i (Z[k] - conj Z[Lh-k]) / 2
+//                  and before the first stage for C2R (fftw-3.3.8/rdft/ct-hc2c.c:59-70 is the CPU path's form of it);
+//                  half the arithmetic and shared-memory traffic of MIXED_R2C / MIXED_C2R.  TileParams::tw_aux = w_2Lh^k,
+//                  k in [0, Lh/2]; the real side is addressed as complex pairs (strides halved by the plan)
+enum { MIXED_C2C = 0, MIXED_R2C = 1, MIXED_C2R = 2, MIXED_R2C_HALF = 3, MIXED_C2R_HALF = 4 };
 
 template <typename T, int P, bool ROWMAP, bool SRC_G, bool DST_G, int IO>
 __device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStages &ms, const void *__restrict__ gin,
@@ -158,25 +165,50 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
     void *__restrict__ gout = reinterpret_cast<char *>(p.out) +
                               (o1 * p.out_os1 + o2 * p.out_os2) * (long long)(IO == MIXED_C2R ? sizeof(T) : sizeof(C));
     const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);
-    const unsigned cmask = (IO == MIXED_C2C && p.inverse) ? 0x80000000u : 0u;
+    const unsigned cmask = ((IO == MIXED_C2C && p.inverse) || IO == MIXED_C2R_HALF) ? 0x80000000u : 0u;
     int sl = (int)threadIdx.x / ms.nfast;
     const int f = (int)threadIdx.x - sl * ms.nfast;
     if (sl >= ms.nslow) sl = 1 << 30;  // threads past nfast * nslow (block rounded up to whole warps) only take part in the barriers
 
+    const C *__restrict__ twx = reinterpret_cast<const C *>(p.tw_aux);  // half-length real modes: w_2L^k
+    const int nfast_line = ms.nfast;
     C *src = buf0, *dst = buf0;
+    if (IO == MIXED_C2R_HALF) {
+        // even/odd pre-pass: half spectrum X[0 .. L] (L = ms.L = half the real length) -> conj(Z'), Z'[k] = Ee + i Oo with
+        // Ee = X[k] + conj X[L-k], Oo = (X[k] - conj X[L-k]) conj(w^k); Z'[L-k] = conj(Ee) + i conj(Oo)
+        for (int w = sl; w < W; w += ms.nslow) {
+            const int wi = min(i0 + w, p.n_inner - 1);
+            const C *g = reinterpret_cast<const C *>(gin) + (long long)wi * p.in_is;
+            C *d = buf0 + w * ms.pitch;
+            for (int k = f; k <= L / 2; k += nfast_line) {
+                const C xa = __ldg(g + k), xb = __ldg(g + (L - k));
+                const C wk = __ldg(twx + k);                       // w^k = c - i s  (wk.x = c, wk.y = -s)
+                const C ee = mk<T>(xa.x + xb.x, xa.y - xb.y);      // X[k] + conj X[L-k]
+                const C dd = mk<T>(xa.x - xb.x, xa.y + xb.y);      // X[k] - conj X[L-k]
+                const C oo = mk<T>(dd.x * wk.x + dd.y * wk.y, dd.y * wk.x - dd.x * wk.y);  // dd * conj(w^k)
+                // Z'[k] = ee + i oo = (ee.x - oo.y, ee.y + oo.x); stored conjugated (backward = conj F conj)
+                d[k] = mk<T>(ee.x - oo.y, -(ee.y + oo.x));
+                // Z'[L-k] = conj(ee) + i conj(oo) = (ee.x + oo.y, -ee.y + oo.x); conjugated
+                if (k > 0) d[L - k] = mk<T>(ee.x + oo.y, ee.y - oo.x);
+            }
+        }
+        __syncthreads();
+        dst = buf1;
+    }
     int Ns = 1;
     for (int s = 0; s < ms.n; ++s) {
         const int P = ms.r[s];
         const C *tws = tw + ms.tw_off[s];
         const unsigned nm = ms.ns_m[s], nsh = ms.ns_s[s];
         const bool first = s == 0, last = s == ms.n - 1;
+        const bool src_g = first && IO != MIXED_C2R_HALF, dst_g = last && IO != MIXED_R2C_HALF;
 #define FFTB200_MIXED_CASE(R)                                                                                        \
     case R:                                                                                                          \
         if constexpr (R <= MAXR) {                                                                                   \
-            if (first && last) mixed_stage<T, R, ROWMAP, true, true, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);        \
-            else if (first) mixed_stage<T, R, ROWMAP, true, false, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);     \
-            else if (last) mixed_stage<T, R, ROWMAP, false, true, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);      \
-            else mixed_stage<T, R, ROWMAP, false, false, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);               \
+            if (src_g && dst_g) mixed_stage<T, R, ROWMAP, true, true, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);   \
+            else if (src_g) mixed_stage<T, R, ROWMAP, true, false, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);  \
+            else if (dst_g) mixed_stage<T, R, ROWMAP, false, true, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);  \
+            else mixed_stage<T, R, ROWMAP, false, false, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);            \
         }                                                                                                            \
         break;
         switch (P) {
@@ -199,7 +231,7 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
                     const char *fin = reinterpret_cast<const char *>(p.in) +
                                       (fo1 * p.in_os1 + fo2 * p.in_os2 + (long long)fi0 * p.in_is) * IN_ELT;
                     const int n_run = ROWMAP ? W : L;                                   // contiguous runs of the tile
-                    const int run_elems = ROWMAP ? (IO == MIXED_C2R ? L / 2 + 1 : L) : W;
+                    const int run_elems = ROWMAP ? (IO == MIXED_C2R ? L / 2 + 1 : (IO == MIXED_C2R_HALF ? L + 1 : L)) : W;
                     const int ch_run = (run_elems * IN_ELT + 127) / 128;                 // 128-byte chunks per run
                     const long long run_stride = ROWMAP ? p.in_is : p.in_ls;
                     for (int ch = (int)threadIdx.x; ch < n_run * ch_run; ch += (int)blockDim.x) {
@@ -211,10 +243,29 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
             }
         }
         Ns *= P;
-        if (!last) __syncthreads();
-        // stage s wrote dst; the next one reads it and writes the other buffer
-        src = dst;
-        dst = (dst == buf0) ? buf1 : buf0;
+        if (!dst_g) {
+            __syncthreads();
+            // stage s wrote dst; the next one reads it and writes the other buffer
+            src = dst;
+            dst = (dst == buf0) ? buf1 : buf0;
+        }
+    }
+    if (IO == MIXED_R2C_HALF) {
+        // even/odd post-pass over the pairs (k, L-k) of Z (in src): X[k] = E + w^k B, X[L-k] = conj(E - w^k B)
+        for (int w = sl; w < W; w += ms.nslow) {
+            if (i0 + w >= p.n_inner) continue;
+            const C *z = src + w * ms.pitch;
+            C *g = reinterpret_cast<C *>(gout) + (long long)(i0 + w) * p.out_is;
+            for (int k = f; k <= L / 2; k += nfast_line) {
+                const C za = z[k], zb = z[k == 0 ? 0 : L - k];
+                const C wk = __ldg(twx + k);                                      // c - i s
+                const C e = mk<T>((T)0.5 * (za.x + zb.x), (T)0.5 * (za.y - zb.y));  // (Z[k] + conj Z[L-k]) / 2
+                const C b = mk<T>((T)0.5 * (za.y + zb.y), (T)-0.5 * (za.x - zb.x));  // -i (Z[k] - conj Z[L-k]) / 2
+                const C wb = cmul(wk, b);
+                g[k] = mk<T>(e.x + wb.x, e.y + wb.y);
+                g[L - k] = mk<T>(e.x - wb.x, -(e.y - wb.y));
+            }
+        }
     }
 }
 

@@ -553,7 +553,9 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     ms.L = L;
     const long long lines0 = lv.empty() ? 1 : std::max<long long>(1, lv[0].n);
     const size_t budget = (size_t)env_int_or("FFTB200_MIXED_TILE_KB", 16) << 10;  // one shared-memory buffer
-    const int nbuf = ms.n >= 3 ? 2 : (ms.n == 2 ? 1 : 0);  // exchanges between stages: ping-pong from three stages on
+    const bool half = io == MIXED_R2C_HALF || io == MIXED_C2R_HALF;  // (L is half the real length; one more shared-memory pass)
+    // exchanges between stages: ping-pong from three stages on; the even/odd pass of the half-length real modes is one more
+    const int nbuf = half ? std::min(2, ms.n) : (ms.n >= 3 ? 2 : (ms.n == 2 ? 1 : 0));
     int W, threads;
     long long lp_sum = 0;
     int lp_max = 0;
@@ -661,7 +663,12 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     ln.mixed_row = row;
     if (io != MIXED_C2C) {
         const unsigned long long lines = ln.algo_bytes / ((unsigned long long)L * ce * 2ull);
-        ln.algo_bytes = lines * ((unsigned long long)L * (ce / 2) + (unsigned long long)(L / 2 + 1) * ce);
+        const unsigned long long lr = half ? 2ull * L : (unsigned long long)L;  // real length of a line
+        ln.algo_bytes = lines * (lr * (ce / 2) + (lr / 2 + 1) * ce);
+    }
+    if (half) {
+        ln.tp.tw_aux = B.table(2ll * L, L / 2 + 1, false);
+        if (!ln.tp.tw_aux) return false;
     }
     ln.tp.tw = dtw;
     ln.tp.prefetch_tiles = 0;
@@ -676,7 +683,7 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     for (int i = 0; i < ms.n; ++i) radices += (i ? "x" : "") + std::to_string((int)ms.r[i]);
     char buf[256];
     snprintf(buf, sizeof buf, "mixed-radix %s %s L=%d (%s) W=%d threads=%d (%d along %s) smem=%d tiles=%u (%s)",
-             io == MIXED_R2C ? "r2c-row" : (io == MIXED_C2R ? "c2r-row" : (row ? "row" : "col")), P->prec ? "fp64" : "fp32", L,
+             io == MIXED_R2C ? "r2c-row" : (io == MIXED_C2R ? "c2r-row" : (io == MIXED_R2C_HALF ? "r2c-row (half-length)" : (io == MIXED_C2R_HALF ? "c2r-row (half-length)" : (row ? "row" : "col")))), P->prec ? "fp64" : "fp32", L,
              radices.c_str(), W, threads, ms.nfast,
              row ? "a line" : "the lines", (int)smem, ln.grid, what);
     ln.desc = buf;
@@ -750,7 +757,14 @@ static bool build_mixed(Builder &B) {
             if (!add_tile_pass(B, V_RR_C2R, (int)(n[last] / 2), 1, 1, lv, cur, BUF_OUT, 0, "axis c2r")) return false;
             P->inplace_ok = false;
         } else {
-            if (!add_mixed_pass(B, true, (int)n[last], 1, 1, lv, cur, BUF_OUT, "axis c2r", MIXED_C2R)) return false;
+            // even length, rows on a pair of reals: half-length complex transform + even/odd pass; else the full-length form
+            bool done = false;
+            if (!(n[last] & 1) && even_out && mixed_axis_ok(n[last] / 2, P->prec) && env_int_or("FFTB200_MIXED_HALF", 1)) {
+                std::vector<Level> lh = lv;
+                for (Level &l : lh) l.os /= 2;
+                done = add_mixed_pass(B, true, (int)(n[last] / 2), 1, 1, lh, cur, BUF_OUT, "axis c2r", MIXED_C2R_HALF);
+            }
+            if (!done && !add_mixed_pass(B, true, (int)n[last], 1, 1, lv, cur, BUF_OUT, "axis c2r", MIXED_C2R)) return false;
             // in place: through the work buffer the input is consumed before the output is written; a direct pass is
             // safe when every CTA's lines occupy the same bytes on both sides (it loads its tile before it stores)
             P->inplace_ok = outer_axes > 1 || P->batch == 1 || P->out_stride[0] == 2 * P->in_stride[0];
@@ -779,7 +793,13 @@ static bool build_mixed(Builder &B) {
             for (Level &l : lv) l.is /= 2;  // input addressed as packed complex pairs
             if (!add_tile_pass(B, V_RR_R2C, (int)(n[last] / 2), 1, 1, lv, BUF_IN, BUF_OUT, 0, "axis r2c")) return false;
         } else {
-            if (!add_mixed_pass(B, true, (int)n[last], 1, 1, lv, BUF_IN, BUF_OUT, "axis r2c", MIXED_R2C)) return false;
+            bool done = false;
+            if (!(n[last] & 1) && even_in && mixed_axis_ok(n[last] / 2, P->prec) && env_int_or("FFTB200_MIXED_HALF", 1)) {
+                std::vector<Level> lh = lv;
+                for (Level &l : lh) l.is /= 2;  // input addressed as packed complex pairs
+                done = add_mixed_pass(B, true, (int)(n[last] / 2), 1, 1, lh, BUF_IN, BUF_OUT, "axis r2c", MIXED_R2C_HALF);
+            }
+            if (!done && !add_mixed_pass(B, true, (int)n[last], 1, 1, lv, BUF_IN, BUF_OUT, "axis r2c", MIXED_R2C)) return false;
         }
         first = false;
     }

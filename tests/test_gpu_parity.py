@@ -831,6 +831,35 @@ def test_inverse_real_transforms(L, oracle):
         assert np.array_equal(Xd.cpu().numpy(), X), "c2r input modified"
 
 
+def test_c2r_mixed_radix_half_and_full_length_forms_agree(L, oracle):
+    """Z2D / C2R of even sizes 2^a 3^b 5^c 7^d: the half-length form (default) and the full-length form give the same
+    reals; odd sizes only have the full-length form."""
+    import os
+    for kind, shape in [("z2d", (1000,)), ("z2d", (12, 10)), ("c2r", (6, 10, 14)), ("z2d", (96, 100, 90)), ("z2d", (4, 6))]:
+        single = kind == "c2r"
+        rdt, cdt = (np.float32, np.complex64) if single else (np.float64, np.complex128)
+        ftype = L.C2R if single else L.Z2D
+        x = oracle.synth(shape, rdt, 1450)
+        X = np.ascontiguousarray(np.fft.rfftn(x.astype(np.float64)).astype(cdt))
+        n_total = int(np.prod(shape))
+        for half in ("1", "0"):
+            os.environ["FFTB200_MIXED_HALF"] = half
+            try:
+                h = L.plan_many(len(shape), list(shape), None, 0, 0, None, 0, 0, ftype, 1)
+            finally:
+                os.environ.pop("FFTB200_MIXED_HALF", None)
+            Xd = torch.from_numpy(X).cuda()
+            yd = torch.zeros(shape, dtype=_torch_dtype(rdt), device="cuda")
+            L.execute(h, ftype, Xd.data_ptr(), yd.data_ptr())
+            torch.cuda.synchronize()
+            desc = L.describe(h)
+            L.destroy(h)
+            assert ("half-length" in desc) == (half == "1"), (shape, half, desc)
+            err = oracle.rel_l2(yd.cpu().numpy() / n_total, x.astype(np.float64))
+            assert err <= 2 * oracle.tolerance(n_total, single), (kind, shape, half, err)
+            assert np.array_equal(Xd.cpu().numpy(), X), "c2r input modified"
+
+
 def test_c2r_in_place_other_sizes(L, oracle):
     """Z2D in place (half spectrum overwritten by the padded real rows) for sizes off the power-of-two path: mixed-radix
     plans where the layouts coincide, the generic plan otherwise - the call must work either way."""
@@ -901,6 +930,21 @@ def test_mixed_radix_lengths_run_one_kernel_per_axis(L, oracle):
         assert "mixed-radix" in desc and "generic" not in desc, (shape, desc)
         err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape))
         assert err <= oracle.tolerance(int(np.prod(shape)), kind == "r2c"), (kind, shape, err)
+    # even last axes run as a half-length complex transform + even/odd pass by default; the full-length form (odd sizes,
+    # odd row offsets) must agree on the same input
+    import os
+    for kind, shape in [("d2z", (1000,)), ("d2z", (12, 10)), ("r2c", (6, 10, 14)), ("d2z", (2,)), ("d2z", (5, 6))]:
+        _, dt_in, _ = _kinds(L)[kind]
+        x = oracle.synth(shape, dt_in, 961)
+        want = cpu_fft(oracle, kind, x, shape)
+        for half in ("1", "0"):
+            os.environ["FFTB200_MIXED_HALF"] = half
+            try:
+                got, desc = gpu_fft(L, kind, x, shape)
+            finally:
+                os.environ.pop("FFTB200_MIXED_HALF", None)
+            assert ("half-length" in desc) == (half == "1" and shape[-1] > 2), (shape, half, desc)
+            assert oracle.rel_l2(got, want) <= oracle.tolerance(int(np.prod(shape)), kind == "r2c"), (kind, shape, half)
     # in-place real input, FFTW's padded layout
     for shape in [(1000,), (30, 90), (12, 10, 18)]:
         ftype = L.D2Z
