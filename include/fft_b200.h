@@ -104,7 +104,7 @@ FFTB200_API int fftb200_exec_d2z(fftb200_handle plan, const void *in, void *out)
 /* Unnormalised inverse of R2C / D2Z (cufftExecC2R / cufftExecZ2D, fftw_plan_dft_c2r semantics): in = packed half
  * spectrum [..][n_last/2+1] complex, out = [..][n_last] reals = n_total * the original data.  The input is
  * preserved (multi-dimensional plans go through a plan-owned work buffer).  Power-of-two sizes run the tiled fast path,
- * sizes 2^a 3^b 5^c 7^d the mixed-radix kernels (one launch per axis), any other size the generic path (Hermitian
+ * sizes 2^a 3^b 5^c 7^d 11^e 13^f the mixed-radix kernels (one launch per axis), any other size the generic path (Hermitian
  * completion, backward complex stages, real part).
  * In-place transforms (in == out): C2C / Z2Z whenever the two layouts coincide; R2C / D2Z (and C2R / Z2D off the
  * power-of-two path) with FFTW's padded in-place layout, i.e. real rows of 2*(n_last/2+1) reals (inembed[last] =

@@ -1,12 +1,12 @@
 // mixed_kernel.cuh — one-pass-per-axis shared-memory FFT for lengths that are NOT powers of two:
-// L = 2^a 3^b 5^c 7^d (96, 100, 120, 360, 384, 480, 1000, 1536, 6000, ...).
+// L = 2^a 3^b 5^c 7^d 11^e 13^f (96, 100, 120, 360, 384, 480, 1000, 1001, 1536, 6000, ...).
 //
 // The power-of-two tile kernels (tile_kernel.cuh) keep R points per thread in registers across all stages and are tuned to
 // the HBM roofline; this kernel is the general form of the same idea for the sizes they do not cover.  A CTA loads a tile
 // of W lines of length L, runs one Stockham autosort stage per radix - the first reading global memory, the last writing
 // it, the exchanges in between through shared memory - and so makes one HBM round trip per axis instead of the generic
 // path's gather + one global-memory pass per prime factor + scatter.  The radices are the in-register DFTs of radix_dft.cuh (2 ... 16,
-// products of 2, 3, 5, 7), chosen at plan time so that a line needs as few stages as possible (1000 = 10 x 10 x 10,
+// products of 2, 3, 5, 7, 11, 13), chosen at plan time so that a line needs as few stages as possible (1000 = 10 x 10 x 10,
 // 384 = 6 x 8 x 8, 96 = 12 x 8); every stage has its own twiddle table, laid out so that a warp reads it as contiguous
 // runs.  The reference's CPU path covers these sizes with FFTW's n1_3 / n1_5 / n1_7 / ... codelets and its generic
 // Cooley-Tukey solver (fftw-3.3.8/dft/ct.c, dft/scalar/codelets/); its own test shapes 3, 5, {3,2,2}, {3,3,2}
@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
         break;
         switch (P) {
             FFTB200_MIXED_CASE(2) FFTB200_MIXED_CASE(3) FFTB200_MIXED_CASE(4) FFTB200_MIXED_CASE(5) FFTB200_MIXED_CASE(6)
-            FFTB200_MIXED_CASE(7) FFTB200_MIXED_CASE(8) FFTB200_MIXED_CASE(9) FFTB200_MIXED_CASE(10) FFTB200_MIXED_CASE(12)
-            FFTB200_MIXED_CASE(14) FFTB200_MIXED_CASE(15) FFTB200_MIXED_CASE(16)
+            FFTB200_MIXED_CASE(7) FFTB200_MIXED_CASE(8) FFTB200_MIXED_CASE(9) FFTB200_MIXED_CASE(10) FFTB200_MIXED_CASE(11)
+            FFTB200_MIXED_CASE(12) FFTB200_MIXED_CASE(13) FFTB200_MIXED_CASE(14) FFTB200_MIXED_CASE(15) FFTB200_MIXED_CASE(16)
             default: break;
         }
 #undef FFTB200_MIXED_CASE
@@ -276,6 +276,6 @@ typedef void (*MixedKernelFn)(const TileParams, const MixedStages);
 // 384^3 fp64 1.62 -> 1.72 ms, 1536^2 0.26 -> 0.34 ms; 1000-point batches unchanged)
 MixedKernelFn mixed_kernel(int prec, bool rowmap, int maxr, int io);
 template <typename T, int MAXR> MixedKernelFn mixed_kernel_inst(bool rowmap, int io);
-constexpr int MIXED_RADICES[] = {16, 15, 14, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+constexpr int MIXED_RADICES[] = {16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
 
 }  // namespace fftb200

@@ -478,7 +478,7 @@ static bool build_fast(Builder &B) {
 }
 
 // ------------------------------------------------------------------------------------------
-// mixed-radix plan: complex transforms with unit element stride whose axes are products of 2, 3, 5 and 7 that fit one
+// mixed-radix plan: transforms with unit element stride whose axes are products of 2, 3, 5, 7, 11 and 13 that fit one
 // shared-memory tile (mixed_kernel.cuh).  One kernel per axis, in place over the output array like the fast plan;
 // power-of-two axes of such a shape still use the tuned tile kernels.  Anything else goes to the generic path.
 // ------------------------------------------------------------------------------------------
@@ -1149,7 +1149,7 @@ int create_plan(Plan **out, int rank, const long long *n, int batch, const long 
         if (!ok) {
             discard();
             if (B.err != FFTB200_SUCCESS) return B.err;
-            ok = build_mixed(B);  // axes of the form 2^a 3^b 5^c 7^d that fit one shared-memory tile
+            ok = build_mixed(B);  // axes of the form 2^a 3^b 5^c 7^d 11^e 13^f that fit one shared-memory tile
         }
         if (!ok) {
             // discard partial fast plan

@@ -1,5 +1,5 @@
 // radix_dft.cuh — in-register forward DFTs (sign -1, natural order in and out) of size
-//     2, 3, 4, 5, 7            written out directly (odd sizes: the conjugate-pair form, (N-1)/2 real root pairs)
+//     2, 3, 4, 5, 7, 11, 13    written out directly (odd sizes: the conjugate-pair form, (N-1)/2 real root pairs)
 //     6, 8, 9, 10, 12, 14, 15, 16   Cooley-Tukey products A x B of the above with the w_N twiddles as compile-time constants
 // for the mixed-radix shared-memory kernel (mixed_kernel.cuh).  All loops unroll and every index is a compile-time
 // constant, so an array argument lives in registers.  They stand where FFTW's n1_3 ... n1_16 / t1_* codelets stand on the
@@ -82,6 +82,8 @@ template <typename T, int P> FFTB200_HD void dft_odd(cplx<T> *a) {
 template <typename T> struct Dft<T, 3> { static FFTB200_HD void run(cplx<T> *a) { dft_odd<T, 3>(a); } };
 template <typename T> struct Dft<T, 5> { static FFTB200_HD void run(cplx<T> *a) { dft_odd<T, 5>(a); } };
 template <typename T> struct Dft<T, 7> { static FFTB200_HD void run(cplx<T> *a) { dft_odd<T, 7>(a); } };
+template <typename T> struct Dft<T, 11> { static FFTB200_HD void run(cplx<T> *a) { dft_odd<T, 11>(a); } };
+template <typename T> struct Dft<T, 13> { static FFTB200_HD void run(cplx<T> *a) { dft_odd<T, 13>(a); } };
 
 // N = A * B.  With n = B n1 + n2 and k = k1 + A k2:  w_N^(n k) = w_A^(n1 k1) * w_N^(n2 k1) * w_B^(n2 k2)
 //   1. for every n2: A-point DFT over n1              -> y[k1][n2]

@@ -45,7 +45,7 @@ template <int N> static int report() {
 int main() {
     int bad = 0;
     bad += report<2>(); bad += report<3>(); bad += report<4>(); bad += report<5>(); bad += report<6>(); bad += report<7>();
-    bad += report<8>(); bad += report<9>(); bad += report<10>(); bad += report<12>(); bad += report<14>(); bad += report<15>();
+    bad += report<8>(); bad += report<9>(); bad += report<10>(); bad += report<11>(); bad += report<12>(); bad += report<13>(); bad += report<14>(); bad += report<15>();
     bad += report<16>();
     return bad;
 }

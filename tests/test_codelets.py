@@ -17,7 +17,7 @@ def test_radix_dfts_match_definition(tmp_path):
                     os.path.join(ROOT, "tests", "src", "codelet_check.cu")], check=True, capture_output=True, timeout=300)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
-    assert sorted(row["n"] for row in rows) == [2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16]
+    assert sorted(row["n"] for row in rows) == [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
     for row in rows:
         assert row["rel_l2_fp64"] < 4e-16 and row["rel_l2_fp32"] < 3e-7, row
     assert r.returncode == 0
@@ -29,7 +29,7 @@ def test_root_table_is_current():
     import re
     txt = open(os.path.join(ROOT, "regent-fft-arjun_b200", "csrc", "dft_roots.inc")).read()
     tabs = re.findall(r"root_(cos|sin)<(\d+)>\(int e\) \{\s*constexpr double t\[\d+\] = \{([^}]*)\}", txt)
-    assert len(tabs) == 22
+    assert len(tabs) == 26
     for fn, n, body in tabs:
         n = int(n)
         vals = [float(v) for v in body.split(",")]

@@ -802,15 +802,15 @@ def test_inverse_real_transforms(L, oracle):
     lib = L.lib()
     assert lib.fftb200_exec_d2z(h, Xd.data_ptr(), yd.data_ptr()) == L.INVALID_TYPE
     L.destroy(h)
-    # sizes that are not powers of two (odd last dimensions included): products of 2, 3, 5, 7 run the mixed-radix kernels
+    # sizes that are not powers of two (odd last dimensions included): products of 2, 3, 5, 7, 11, 13 run the mixed-radix kernels
     # (Hermitian completion while loading the last axis), anything else the generic path (Hermitian completion of the
     # half spectrum, backward complex stages - Bluestein for large primes - real part out)
     for i, (kind, shape, tag) in enumerate([("z2d", (12,), "mixed-radix c2r-row"), ("z2d", (12, 10), "mixed-radix c2r-row"),
                                             ("c2r", (3, 5, 6), "mixed-radix c2r-row"), ("z2d", (1000,), "mixed-radix c2r-row"),
-                                            ("z2d", (7, 33), "Hermitian"), ("z2d", (5, 4, 9), "mixed-radix c2r-row"),
+                                            ("z2d", (7, 33), "mixed-radix c2r-row"), ("z2d", (7, 34), "Hermitian"), ("z2d", (5, 4, 9), "mixed-radix c2r-row"),
                                             ("z2d", (1021,), "Hermitian"), ("c2r", (6, 127), "Hermitian"),
                                             ("z2d", (9, 7), "mixed-radix c2r-row"), ("z2d", (96, 100, 90), "mixed-radix c2r-row"),
-                                            ("c2r", (15, 1001), "Hermitian"), ("z2d", (6, 1024), "c2r-row"),
+                                            ("c2r", (15, 1001), "mixed-radix c2r-row"), ("z2d", (6, 1024), "c2r-row"),
                                             ("z2d", (128, 6), "mixed-radix c2r-row")]):
         single = kind == "c2r"
         rdt, cdt = (np.float32, np.complex64) if single else (np.float64, np.complex128)
@@ -893,7 +893,7 @@ def test_large_prime_lengths_use_bluestein(L, oracle):
         if kind in ("z2z", "c2c"):
             back, _ = gpu_fft(L, kind, got, shape, direction=+1)
             assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * oracle.tolerance(int(np.prod(shape)), kind == "c2c")
-    for kind, shape in [("z2z", (11, 13)), ("z2z", (2 * 3 * 11,)), ("z2z", (31 * 4,)), ("d2z", (3, 11, 2)), ("d2z", (1300,))]:
+    for kind, shape in [("z2z", (17, 19)), ("z2z", (2 * 3 * 17,)), ("z2z", (31 * 4,)), ("d2z", (3, 17, 2)), ("d2z", (1700,))]:
         _, dt_in, _ = _kinds(L)[kind]
         x = oracle.synth(shape, dt_in, 995)
         got, desc = gpu_fft(L, kind, x, shape)
@@ -902,7 +902,7 @@ def test_large_prime_lengths_use_bluestein(L, oracle):
 
 
 def test_mixed_radix_lengths_run_one_kernel_per_axis(L, oracle):
-    """Complex transforms whose axes are products of 2, 3, 5 and 7 (the reference's own 3, 5, {3,2,2}, {3,3,2}:
+    """Transforms whose axes are products of 2, 3, 5, 7, 11 and 13 (the reference's own 3, 5, {3,2,2}, {3,3,2}:
     test/fft_test.rg:143,247,328,349; FFTW's n1_3 / n1_5 / n1_7 codelets on the CPU path) run as ONE shared-memory
     kernel per axis (mixed_kernel.cuh), power-of-two axes of such shapes on the tuned tile kernels.  Forward against
     FFTW, backward round trip, in place, batched, both precisions."""
@@ -910,7 +910,7 @@ def test_mixed_radix_lengths_run_one_kernel_per_axis(L, oracle):
              ("z2z", (360,)), ("z2z", (1000,)), ("z2z", (1536,)), ("z2z", (5040,)), ("z2z", (6000,)), ("c2c", (3 * 4096,)),
              ("z2z", (3, 2, 2)), ("z2z", (3, 3, 2)), ("z2z", (96, 96)), ("z2z", (100, 60)), ("z2z", (7, 1024)),
              ("z2z", (1024, 9)), ("c2c", (45, 50)), ("z2z", (96, 96, 96)), ("z2z", (60, 64, 100)), ("c2c", (30, 42, 70)),
-             ("z2z", (1, 15)), ("z2z", (15, 1))]
+             ("z2z", (1, 15)), ("z2z", (15, 1)), ("z2z", (1001,)), ("z2z", (11, 13)), ("c2c", (143, 22)), ("z2z", (11 * 13 * 16,))]
     for kind, shape in cases:
         _, dt_in, _ = _kinds(L)[kind]
         x = oracle.synth(shape, dt_in, 940 + len(shape))
@@ -923,7 +923,7 @@ def test_mixed_radix_lengths_run_one_kernel_per_axis(L, oracle):
         assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * tol, (kind, shape)
     # real input: the last axis reads reals and stores the first n/2+1 outputs; the other axes run over those columns
     for kind, shape in [("d2z", (3,)), ("d2z", (6,)), ("d2z", (9,)), ("d2z", (1000,)), ("r2c", (1000,)), ("d2z", (3, 3, 2)),
-                        ("d2z", (96, 96, 96)), ("r2c", (60, 64, 100)), ("d2z", (100, 512)), ("d2z", (7, 15)), ("d2z", (45, 2))]:
+                        ("d2z", (96, 96, 96)), ("r2c", (60, 64, 100)), ("d2z", (100, 512)), ("d2z", (7, 15)), ("d2z", (45, 2)), ("d2z", (26, 22)), ("r2c", (1001,))]:
         _, dt_in, _ = _kinds(L)[kind]
         x = oracle.synth(shape, dt_in, 960 + len(shape))
         got, desc = gpu_fft(L, kind, x, shape)
@@ -979,7 +979,7 @@ def test_mixed_radix_lengths_run_one_kernel_per_axis(L, oracle):
         L.destroy(h)
         assert oracle.rel_l2(buf.cpu().numpy(), cpu_fft(oracle, "z2z", x, shape)) <= oracle.tolerance(int(np.prod(shape)), False)
     # lengths past one shared-memory tile, or with other primes, stay on the generic path
-    for shape in [(4 * 5 ** 5,), (11 * 8,)]:
+    for shape in [(4 * 5 ** 5,), (17 * 8,)]:
         _, dt_in, _ = _kinds(L)["z2z"]
         x = oracle.synth(shape, dt_in, 955)
         got, desc = gpu_fft(L, "z2z", x, shape)
