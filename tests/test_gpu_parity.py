@@ -831,6 +831,40 @@ def test_inverse_real_transforms(L, oracle):
         assert np.array_equal(Xd.cpu().numpy(), X), "c2r input modified"
 
 
+def test_mixed_radix_randomized_shapes(L, oracle):
+    """Seeded sweep over 1-3-D shapes with axes drawn from products of 2, 3, 5, 7, 11, 13 (ragged tiles, one to five
+    stages, single-radix axes, batches), every transform kind, against the oracle.  Whatever plan the builder picks must
+    be right; the sweep also counts how many of them took the mixed-radix kernels."""
+    rng = np.random.default_rng(20260)
+    axes = [3, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15, 18, 20, 21, 22, 24, 26, 28, 30, 33, 35, 36, 39, 40, 42, 45, 48, 50, 54,
+            55, 56, 60, 63, 65, 66, 70, 72, 75, 77, 80, 84, 90, 91, 96, 98, 99, 100, 104, 108, 110, 112, 117, 120, 125, 126,
+            130, 132, 135, 140, 143, 144, 147, 150, 154, 156, 160, 162, 165, 168, 169, 175, 176, 180, 182, 189, 192, 195,
+            196, 198, 200, 208, 210, 216, 220, 224, 225, 231, 234, 240, 242, 243, 245, 250, 252, 260, 264, 270, 273, 275,
+            280, 286, 288, 294, 297, 300, 343, 363, 375, 390, 420, 441, 462, 480, 500, 507, 539, 546, 600, 625, 630, 637,
+            686, 720, 726, 729, 750, 840, 845, 847, 875, 900, 945, 960, 1000, 1001, 1014, 1029, 1050, 1078, 1080, 1125,
+            1155, 1183, 1200, 1250, 1260, 1331, 1350, 1372, 1440, 1452, 1500, 1521, 1536, 1575, 1694, 1715, 1800, 1859, 2000,
+            2197, 2310, 2401, 2500, 2520, 3000, 3125, 3430, 3600, 3993, 4000, 4116, 4375, 5000, 5040, 6000, 6250]
+    n_mixed = 0
+    for case in range(72):
+        rank = int(rng.integers(1, 4))
+        cap = {1: 6250, 2: 400, 3: 60}[rank]
+        pool = [a for a in axes if a <= cap]
+        shape = tuple(int(rng.choice(pool)) for _ in range(rank))
+        kind = ["z2z", "c2c", "d2z", "r2c"][case % 4]
+        batch = int(rng.choice([1, 1, 2, 5])) if np.prod(shape) < 50000 else 1
+        _, dt_in, _ = _kinds(L)[kind]
+        x = oracle.synth(((batch,) if batch > 1 else ()) + shape, dt_in, 3000 + case)
+        got, desc = gpu_fft(L, kind, x, shape, batch=batch)
+        n_mixed += "mixed-radix" in desc
+        tol = oracle.tolerance(int(np.prod(shape)), kind in ("c2c", "r2c"))
+        err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape, batch=batch))
+        assert err <= tol, (kind, shape, batch, err, desc)
+        if kind in ("z2z", "c2c"):
+            back, _ = gpu_fft(L, kind, got, shape, batch=batch, direction=+1)
+            assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * tol, (kind, shape, batch, "round trip")
+    assert n_mixed >= 60, n_mixed
+
+
 def test_c2r_mixed_radix_half_and_full_length_forms_agree(L, oracle):
     """Z2D / C2R of even sizes 2^a 3^b 5^c 7^d: the half-length form (default) and the full-length form give the same
     reals; odd sizes only have the full-length form."""
