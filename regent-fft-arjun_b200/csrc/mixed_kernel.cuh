@@ -109,9 +109,12 @@ __device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStag
                 for (int t = 0; t < P; ++t) a[t] = s[t * Lp * s_elem];
             }
             if (Ns > 1) {
-                const C *twk = tws + k;
+                // (byte offsets: one 32 x 32 + 64-bit multiply-add per address)
+                const char *twk = reinterpret_cast<const char *>(tws + k);
+                const unsigned stepb = (unsigned)Ns * (unsigned)sizeof(C);
 #pragma unroll
-                for (int t = 1; t < P; ++t) a[t] = cmul(a[t], __ldg(twk + (unsigned)((t - 1) * Ns)));
+                for (int t = 1; t < P; ++t)
+                    a[t] = cmul(a[t], __ldg(reinterpret_cast<const C *>(twk + (unsigned long long)((unsigned)(t - 1) * stepb))));
             }
             Dft<T, P>::run(a);
             if (DST_G) {
