@@ -11,7 +11,7 @@ template <typename T> static MixedKernelFn pick(bool rowmap, int maxr, int io) {
 }
 
 MixedKernelFn mixed_kernel(int prec, bool rowmap, int maxr, int io) {
-    if (io != MIXED_C2C && !rowmap) return nullptr;
+    if (rowmap ? io == MIXED_TW : (io != MIXED_C2C && io != MIXED_TW)) return nullptr;
     return prec ? pick<double>(rowmap, maxr, io) : pick<float>(rowmap, maxr, io);
 }
 

@@ -55,7 +55,12 @@ struct MixedStages {
 //                  and before the first stage for C2R (fftw-3.3.8/rdft/ct-hc2c.c:59-70 is the CPU path's form of it);
 //                  half the arithmetic and shared-memory traffic of MIXED_R2C / MIXED_C2R.  TileParams::tw_aux = w_2Lh^k,
 //                  k in [0, Lh/2]; the real side is addressed as complex pairs (strides halved by the plan)
-enum { MIXED_C2C = 0, MIXED_R2C = 1, MIXED_C2R = 2, MIXED_R2C_HALF = 3, MIXED_C2R_HALF = 4 };
+//   Two-pass lines (L = N1 N2 too long for one tile; n = n1 N2 + n2, k = k1 + N1 k2; fftw-3.3.8/dft/ct.c is the CPU form):
+//       MIXED_TW   strided pass over n1 whose store multiplies row k1, column n2 by w_L^(k1 n2) (two-level table
+//                  TileParams::tw4_hi / tw4_lo, fp64), into the work buffer
+//       MIXED_RC   contiguous pass over n2 of the work buffer's rows; the last stage stays in shared memory and a final
+//                  pass with the adjacent lines as the fast thread index stores out[k2 N1 + k1] in 128-byte runs
+enum { MIXED_C2C = 0, MIXED_R2C = 1, MIXED_C2R = 2, MIXED_R2C_HALF = 3, MIXED_C2R_HALF = 4, MIXED_TW = 5, MIXED_RC = 6 };
 
 template <typename T, int P, bool ROWMAP, bool SRC_G, bool DST_G, int IO>
 __device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStages &ms, const void *__restrict__ gin,
@@ -136,6 +141,16 @@ __device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStag
                     } else {
                         C *g = reinterpret_cast<C *>(gout) + (i0 + w);
                         const unsigned ls = (unsigned)p.out_ls;
+                        if (IO == MIXED_TW) {
+                            const unsigned col = (unsigned)(i0 + w);
+#pragma unroll
+                            for (int t = 0; t < P; ++t) {
+                                const unsigned m = (unsigned)(ob + t * Ns) * col;  // < L
+                                const double2 wh = __ldg(p.tw4_hi + (m >> p.tw4_shift)), wl = __ldg(p.tw4_lo + (m & p.tw4_mask));
+                                const C wv = mk<T>((T)(wh.x * wl.x - wh.y * wl.y), (T)(wh.x * wl.y + wh.y * wl.x));
+                                a[t] = cmul(a[t], wv);
+                            }
+                        }
 #pragma unroll
                         for (int t = 0; t < P; ++t) g[(unsigned)(ob + t * Ns) * ls] = conj_if(a[t], cmask);
                     }
@@ -161,14 +176,14 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
     const int o = fast_div(tile, p.div_tpo_m, p.div_tpo_s);
     const int i0 = (tile - o * p.tiles_per_outer) * W;
     const int o1 = fast_div(o, p.div_o2_m, p.div_o2_s), o2 = o - o1 * p.n_o2;
-    static_assert(IO == MIXED_C2C || ROWMAP, "real transforms: contiguous axis only");
+    static_assert(IO == MIXED_C2C || (IO == MIXED_TW ? !ROWMAP : ROWMAP), "real transforms and the transposing pass: contiguous axis; twiddled store: strided axis");
     // (the real side of a real transform is addressed in real elements)
     const void *__restrict__ gin = reinterpret_cast<const char *>(p.in) +
                                    (o1 * p.in_os1 + o2 * p.in_os2) * (long long)(IO == MIXED_R2C ? sizeof(T) : sizeof(C));
     void *__restrict__ gout = reinterpret_cast<char *>(p.out) +
                               (o1 * p.out_os1 + o2 * p.out_os2) * (long long)(IO == MIXED_C2R ? sizeof(T) : sizeof(C));
     const C *__restrict__ tw = reinterpret_cast<const C *>(p.tw);
-    const unsigned cmask = ((IO == MIXED_C2C && p.inverse) || IO == MIXED_C2R_HALF) ? 0x80000000u : 0u;
+    const unsigned cmask = (((IO == MIXED_C2C || IO == MIXED_TW || IO == MIXED_RC) && p.inverse) || IO == MIXED_C2R_HALF) ? 0x80000000u : 0u;
     int sl = (int)threadIdx.x / ms.nfast;
     const int f = (int)threadIdx.x - sl * ms.nfast;
     if (sl >= ms.nslow) sl = 1 << 30;  // threads past nfast * nslow (block rounded up to whole warps) only take part in the barriers
@@ -204,7 +219,7 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
         const C *tws = tw + ms.tw_off[s];
         const unsigned nm = ms.ns_m[s], nsh = ms.ns_s[s];
         const bool first = s == 0, last = s == ms.n - 1;
-        const bool src_g = first && IO != MIXED_C2R_HALF, dst_g = last && IO != MIXED_R2C_HALF;
+        const bool src_g = first && IO != MIXED_C2R_HALF, dst_g = last && IO != MIXED_R2C_HALF && IO != MIXED_RC;
 #define FFTB200_MIXED_CASE(R)                                                                                        \
     case R:                                                                                                          \
         if constexpr (R <= MAXR) {                                                                                   \
@@ -251,6 +266,17 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
             // stage s wrote dst; the next one reads it and writes the other buffer
             src = dst;
             dst = (dst == buf0) ? buf1 : buf0;
+        }
+    }
+    if (IO == MIXED_RC) {
+        // transposing store: the W adjacent lines are the fast thread index (out_is == 1), element l of a line goes
+        // out_ls further; the odd line pitch keeps the shared-memory reads free of bank conflicts
+        const int fw = (int)threadIdx.x % W, fl = (int)threadIdx.x / W, nl = (int)blockDim.x / W;
+        if (fl < nl && i0 + fw < p.n_inner) {
+            C *g = reinterpret_cast<C *>(gout) + (i0 + fw);
+            const C *z = src + fw * ms.pitch;
+            const unsigned ls = (unsigned)p.out_ls;
+            for (int l = fl; l < L; l += nl) g[(unsigned)l * ls] = conj_if(z[l], cmask);
         }
     }
     if (IO == MIXED_R2C_HALF) {

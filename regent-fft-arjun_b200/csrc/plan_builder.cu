@@ -536,10 +536,11 @@ static bool mixed_axis_ok(long long L, int prec) {
 }
 
 // io: MIXED_C2C, or (contiguous axis only) MIXED_R2C / MIXED_C2R with the real side's strides in real elements
+//     MIXED_TW (strided axis; twN = length of the whole two-pass line) / MIXED_RC (contiguous load, transposing store)
 static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long long out_ls, std::vector<Level> lv, int src,
-                           int dst, const char *what, int io = MIXED_C2C) {
+                           int dst, const char *what, int io = MIXED_C2C, long long twN = 0) {
     Plan *P = B.P;
-    if (io != MIXED_C2C && !row) return false;
+    if (row ? io == MIXED_TW : (io != MIXED_C2C && io != MIXED_TW)) return false;
     const size_t ce = P->prec ? 16 : 8;
     const int maxr = mixed_max_radix(P->prec);
     const std::vector<int> rad = mixed_radices(L, maxr);
@@ -555,7 +556,8 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     const size_t budget = (size_t)env_int_or("FFTB200_MIXED_TILE_KB", 16) << 10;  // one shared-memory buffer
     const bool half = io == MIXED_R2C_HALF || io == MIXED_C2R_HALF;  // (L is half the real length; one more shared-memory pass)
     // exchanges between stages: ping-pong from three stages on; the even/odd pass of the half-length real modes is one more
-    const int nbuf = half ? std::min(2, ms.n) : (ms.n >= 3 ? 2 : (ms.n == 2 ? 1 : 0));
+    const bool stay = half || io == MIXED_RC;  // one more pass over shared memory after (or before) the stages
+    const int nbuf = stay ? std::min(2, ms.n) : (ms.n >= 3 ? 2 : (ms.n == 2 ? 1 : 0));
     int W, threads;
     long long lp_sum = 0;
     int lp_max = 0;
@@ -578,17 +580,26 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
         const int hi = std::min(lp_max, MIXED_MAX_THREADS), lo = std::min(hi, 8);
         double best = -1;
         int tl = hi, nslow = 1;
+        // (transposing store: the tile is as wide as a strided-axis tile - 128-byte runs - whatever the line slots are)
+        int w_rc = (int)(128 / ce);
+        while (w_rc > 1 && (size_t)w_rc * line_bytes > MIXED_SMEM_MAX) w_rc /= 2;
         for (int c = lo; c <= hi; ++c) {
             long long ns = std::min<long long>(std::max(1, MIXED_MAX_THREADS / c), lines0);
             ns = std::min<long long>(ns, std::max<size_t>(1, (64u << 10) / line_bytes));
+            if (io == MIXED_RC) {
+                long long p2 = 1;
+                while (p2 * 2 <= std::min<long long>(std::max(1, MIXED_MAX_THREADS / c), w_rc)) p2 *= 2;
+                ns = p2;
+            }
             const int bt = (int)((c * ns + 31) / 32 * 32);
-            const double sc = score(c, (int)(c * ns), bt, nbuf ? line_bytes * ns : 0);
+            const double sc = score(c, (int)(c * ns), bt, nbuf ? line_bytes * (io == MIXED_RC ? w_rc : ns) : 0);
             if (sc >= best) { best = sc; tl = c; nslow = (int)ns; }
         }
         // small tiles: several rounds of nslow lines per CTA, up to the tile budget
         int rounds = (int)std::max<size_t>(1, budget / ((size_t)ms.pitch * ce * nslow));
         rounds = (int)std::min<long long>(rounds, std::max<long long>(1, lines0 / nslow));
         while (rounds > 1 && line_bytes * nslow * rounds > MIXED_SMEM_MAX) --rounds;
+        if (io == MIXED_RC) rounds = std::max(1, w_rc / nslow);
         W = nslow * rounds;
         ms.nfast = tl;
         ms.nslow = nslow;
@@ -655,7 +666,7 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     // (the opt-in shared-memory limit is a property of the kernel, shared by every plan: always raise it to the maximum)
     ki->smem_bytes = (int)MIXED_SMEM_MAX;
     ki->cluster = 1;
-    if (!add_tile_pass_with(B, ki.get(), row ? V_RR : V_CC, L, in_ls, out_ls, lv, src, dst, 0, what)) return false;
+    if (!add_tile_pass_with(B, ki.get(), io == MIXED_RC ? V_RC : (row ? V_RR : V_CC), L, in_ls, out_ls, lv, src, dst, 0, what)) return false;
     ki->smem_bytes = (int)smem;
     Launch &ln = P->launches.back();
     ln.kind = Launch::MIXED;
@@ -670,6 +681,15 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
         ln.tp.tw_aux = B.table(2ll * L, L / 2 + 1, false);
         if (!ln.tp.tw_aux) return false;
     }
+    if (io == MIXED_TW) {
+        // w_twN^m = hi[m >> sh] * lo[m & mask], both tables fp64
+        const int bits = ilog2ll(twN) + 1, sh = (bits + 1) / 2;
+        ln.tp.tw4_shift = sh;
+        ln.tp.tw4_mask = (1 << sh) - 1;
+        ln.tp.tw4_lo = (const double2 *)B.table(twN, 1ll << sh, true);
+        ln.tp.tw4_hi = (const double2 *)B.table(twN, (twN >> sh) + 1, true, 1ll << sh);
+        if (!ln.tp.tw4_lo || !ln.tp.tw4_hi) return false;
+    }
     ln.tp.tw = dtw;
     ln.tp.prefetch_tiles = 0;
     if (env_int_or("FFTB200_MIXED_PREFETCH", 1) != 0) {
@@ -683,7 +703,7 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     for (int i = 0; i < ms.n; ++i) radices += (i ? "x" : "") + std::to_string((int)ms.r[i]);
     char buf[256];
     snprintf(buf, sizeof buf, "mixed-radix %s %s L=%d (%s) W=%d threads=%d (%d along %s) smem=%d tiles=%u (%s)",
-             io == MIXED_R2C ? "r2c-row" : (io == MIXED_C2R ? "c2r-row" : (io == MIXED_R2C_HALF ? "r2c-row (half-length)" : (io == MIXED_C2R_HALF ? "c2r-row (half-length)" : (row ? "row" : "col")))), P->prec ? "fp64" : "fp32", L,
+             io == MIXED_R2C ? "r2c-row" : (io == MIXED_C2R ? "c2r-row" : (io == MIXED_R2C_HALF ? "r2c-row (half-length)" : (io == MIXED_C2R_HALF ? "c2r-row (half-length)" : (io == MIXED_TW ? "col+twiddle" : (io == MIXED_RC ? "row->col" : (row ? "row" : "col")))))), P->prec ? "fp64" : "fp32", L,
              radices.c_str(), W, threads, ms.nfast,
              row ? "a line" : "the lines", (int)smem, ln.grid, what);
     ln.desc = buf;
@@ -700,12 +720,39 @@ static bool build_mixed(Builder &B) {
     const bool real = P->real, c2r = P->c2r;
     const int maxL = max_tile_length(P->prec);
     long long total = 1;
+    int long_axes = 0, short_axes = 0;
     for (int d = 0; d < rank; ++d) {
         total *= n[d];
         if (n[d] == 1) continue;
-        if (!(is_pow2(n[d]) && n[d] <= maxL) && !mixed_axis_ok(n[d], P->prec)) return false;
+        if ((is_pow2(n[d]) && n[d] <= maxL) || mixed_axis_ok(n[d], P->prec)) ++short_axes; else ++long_axes;
     }
     if (total == 1) return false;
+    if (long_axes == 1 && short_axes == 0 && n[last] > 1 && !real && !c2r) {
+        // a single line too long for one tile: L = N1 N2, a strided pass over n1 with the w_L^(k1 n2) twiddle into a work
+        // buffer, then a contiguous pass over n2 with a transposing store (both factors as balanced as the radices allow)
+        const long long Lw = n[last];
+        if (Lw > (1ll << 31) - 1) return false;
+        long long N1 = 0;
+        for (long long a = (long long)std::sqrt((double)Lw) + 1; a >= 2; --a) {
+            if (Lw % a) continue;
+            if (mixed_axis_ok(a, P->prec) && mixed_axis_ok(Lw / a, P->prec)) { N1 = a; break; }
+        }
+        if (!N1) return false;
+        const long long N2 = Lw / N1;  // N1 <= N2: the strided pass (whole 128-byte columns in shared memory) gets the shorter factor
+        const size_t ce = P->prec ? 16 : 8;
+        P->work_bytes = (size_t)Lw * P->batch * ce;
+        P->work[0] = B.alloc(P->work_bytes);
+        if (!P->work[0]) return false;
+        if (!add_mixed_pass(B, false, (int)N1, N2, N2, {{N2, 1, 1}, {(long long)P->batch, P->in_stride[0], Lw}}, BUF_IN, BUF_WORK0,
+                            "two-pass line 1/2", MIXED_TW, Lw))
+            return false;
+        if (!add_mixed_pass(B, true, (int)N2, 1, N1, {{N1, N2, 1}, {(long long)P->batch, Lw, P->out_stride[0]}}, BUF_WORK0, BUF_OUT,
+                            "two-pass line 2/2", MIXED_RC))
+            return false;
+        P->inplace_ok = true;  // every pass goes through the work buffer
+        return true;
+    }
+    if (long_axes) return false;
     if ((real || c2r) && n[last] < 2) return false;
     const long long nc = n[last] / 2 + 1;
     // one pass along `axis`: the tuned power-of-two tile kernel when there is one, else the mixed-radix kernel

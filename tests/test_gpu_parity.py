@@ -831,6 +831,34 @@ def test_inverse_real_transforms(L, oracle):
         assert np.array_equal(Xd.cpu().numpy(), X), "c2r input modified"
 
 
+def test_long_mixed_radix_lines_run_two_passes(L, oracle):
+    """1-D lengths 2^a 3^b 5^c 7^d 11^e 13^f too long for one shared-memory tile (10^4 ... 2 * 10^6 points): L = N1 N2, a
+    strided pass with the w_L^(k1 n2) twiddle into a work buffer, then a contiguous pass with a transposing store
+    (fftw-3.3.8/dft/ct.c is the CPU path's decomposition) - two HBM round trips instead of one per prime factor.
+    Forward against FFTW, round trip, batches, in place."""
+    for kind, shape, batch in [("z2z", (10000,), 1), ("z2z", (100000,), 1), ("z2z", (1000000,), 1), ("c2c", (1000000,), 1),
+                               ("z2z", (20000,), 3), ("c2c", (65536 * 3,), 2), ("z2z", (7 * 11 * 13 * 100,), 1),
+                               ("z2z", (2000000,), 1), ("z2z", (6561 * 2,), 5)]:
+        _, dt_in, _ = _kinds(L)[kind]
+        x = oracle.synth(((batch,) if batch > 1 else ()) + shape, dt_in, 1700 + batch)
+        got, desc = gpu_fft(L, kind, x, shape, batch=batch)
+        assert "col+twiddle" in desc and "row->col" in desc and "generic" not in desc, (shape, desc)
+        tol = oracle.tolerance(int(np.prod(shape)), kind == "c2c")
+        err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape, batch=batch))
+        assert err <= tol, (kind, shape, batch, err)
+        back, _ = gpu_fft(L, kind, got, shape, batch=batch, direction=+1)
+        assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * tol, (kind, shape, "round trip")
+    # in place
+    ftype, dt_in, _ = _kinds(L)["z2z"]
+    x = oracle.synth((30000,), dt_in, 1710)
+    buf = torch.from_numpy(x.copy()).cuda()
+    h = L.plan_many(1, [30000], None, 0, 0, None, 0, 0, ftype, 1)
+    L.execute(h, ftype, buf.data_ptr(), buf.data_ptr())
+    torch.cuda.synchronize()
+    L.destroy(h)
+    assert oracle.rel_l2(buf.cpu().numpy(), cpu_fft(oracle, "z2z", x, (30000,))) <= oracle.tolerance(30000, False)
+
+
 def test_mixed_radix_randomized_shapes(L, oracle):
     """Seeded sweep over 1-3-D shapes with axes drawn from products of 2, 3, 5, 7, 11, 13 (ragged tiles, one to five
     stages, single-radix axes, batches), every transform kind, against the oracle.  Whatever plan the builder picks must
@@ -1012,8 +1040,8 @@ def test_mixed_radix_lengths_run_one_kernel_per_axis(L, oracle):
         torch.cuda.synchronize()
         L.destroy(h)
         assert oracle.rel_l2(buf.cpu().numpy(), cpu_fft(oracle, "z2z", x, shape)) <= oracle.tolerance(int(np.prod(shape)), False)
-    # lengths past one shared-memory tile, or with other primes, stay on the generic path
-    for shape in [(4 * 5 ** 5,), (17 * 8,)]:
+    # long axes of multi-dimensional shapes, and other primes, stay on the generic path
+    for shape in [(4 * 5 ** 5, 2), (17 * 8,)]:
         _, dt_in, _ = _kinds(L)["z2z"]
         x = oracle.synth(shape, dt_in, 955)
         got, desc = gpu_fft(L, "z2z", x, shape)
