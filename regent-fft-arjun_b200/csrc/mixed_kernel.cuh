@@ -35,6 +35,7 @@ struct MixedStages {
     int nfast;      // ROWMAP: threads along a line; else W (the adjacent lines are the fast thread index)
     int nslow;      // blockDim.x / nfast
     int pitch;      // ROWMAP: shared-memory elements between consecutive lines of the tile
+    int tw_o2;      // MIXED_TW: the column index n2 of the twiddle w_L^(k1 n2) is the tile's o2 index (else its line index)
     unsigned char r[MIXED_MAX_STAGES];   // radix of each stage, product = L
     int tw_off[MIXED_MAX_STAGES];        // stage s: table at tw + tw_off[s], entry [(t-1)*Ns + k] = w_L^(t k L / (Ns P))
     unsigned ns_m[MIXED_MAX_STAGES], ns_s[MIXED_MAX_STAGES];  // fast_div constants of Ns
@@ -67,7 +68,7 @@ __device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStag
                                             void *__restrict__ gout, const cplx<T> *__restrict__ ssrc,
                                             cplx<T> *__restrict__ sdst, const cplx<T> *__restrict__ tws, const int Ns,
                                             const unsigned nm, const unsigned nsh, const int i0, const int f, const int sl,
-                                            const unsigned cmask) {
+                                            const unsigned cmask, const int o2) {
     using C = cplx<T>;
     const int Lp = ms.L / P;
     const int W = ms.W;
@@ -142,7 +143,7 @@ __device__ __forceinline__ void mixed_stage(const TileParams &p, const MixedStag
                         C *g = reinterpret_cast<C *>(gout) + (i0 + w);
                         const unsigned ls = (unsigned)p.out_ls;
                         if (IO == MIXED_TW) {
-                            const unsigned col = (unsigned)(i0 + w);
+                            const unsigned col = ms.tw_o2 ? (unsigned)o2 : (unsigned)(i0 + w);
 #pragma unroll
                             for (int t = 0; t < P; ++t) {
                                 const unsigned m = (unsigned)(ob + t * Ns) * col;  // < L
@@ -223,10 +224,10 @@ __global__ void __launch_bounds__(MIXED_MAX_THREADS) fft_mixed_kernel(const Tile
 #define FFTB200_MIXED_CASE(R)                                                                                        \
     case R:                                                                                                          \
         if constexpr (R <= MAXR) {                                                                                   \
-            if (src_g && dst_g) mixed_stage<T, R, ROWMAP, true, true, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);   \
-            else if (src_g) mixed_stage<T, R, ROWMAP, true, false, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);  \
-            else if (dst_g) mixed_stage<T, R, ROWMAP, false, true, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);  \
-            else mixed_stage<T, R, ROWMAP, false, false, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask);            \
+            if (src_g && dst_g) mixed_stage<T, R, ROWMAP, true, true, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask, o2);   \
+            else if (src_g) mixed_stage<T, R, ROWMAP, true, false, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask, o2);  \
+            else if (dst_g) mixed_stage<T, R, ROWMAP, false, true, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask, o2);  \
+            else mixed_stage<T, R, ROWMAP, false, false, IO>(p, ms, gin, gout, src, dst, tws, Ns, nm, nsh, i0, f, sl, cmask, o2);            \
         }                                                                                                            \
         break;
         switch (P) {

@@ -138,8 +138,9 @@ static void merge_levels(std::vector<Level> &lv) {
     for (size_t i = 0; i < lv.size(); ++i) {
         const Level &l = lv[i];
         // a unit-stride level of extent 1 stays: it is the tile's inner index (ragged last chunk of a slab pass)
-        if (l.n == 1 && !(i == 0 && l.is == 1 && l.os == 1 && lv.size() > 1)) continue;
-        if (!out.empty() && l.is == out.back().n * out.back().is && l.os == out.back().n * out.back().os)
+        if (l.n == 1 && !l.keep && !(i == 0 && l.is == 1 && l.os == 1 && lv.size() > 1)) continue;
+        if (!out.empty() && !l.keep && !out.back().keep && l.is == out.back().n * out.back().is &&
+            l.os == out.back().n * out.back().os)
             out.back().n *= l.n;
         else
             out.push_back(l);
@@ -538,8 +539,13 @@ static bool mixed_axis_ok(long long L, int prec) {
 // io: MIXED_C2C, or (contiguous axis only) MIXED_R2C / MIXED_C2R with the real side's strides in real elements
 //     MIXED_TW (strided axis; twN = length of the whole two-pass line) / MIXED_RC (contiguous load, transposing store)
 static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long long out_ls, std::vector<Level> lv, int src,
-                           int dst, const char *what, int io = MIXED_C2C, long long twN = 0) {
+                           int dst, const char *what, int io = MIXED_C2C, long long twN = 0, bool tw_o2 = false) {
     Plan *P = B.P;
+    if (tw_o2) {
+        // the twiddle's column index must survive as the tile's o2 index
+        merge_levels(lv);
+        if (lv.size() < 2 || lv.size() > 3 || !lv[1].keep) return false;
+    }
     if (row ? io == MIXED_TW : (io != MIXED_C2C && io != MIXED_TW)) return false;
     const size_t ce = P->prec ? 16 : 8;
     const int maxr = mixed_max_radix(P->prec);
@@ -552,6 +558,7 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     MixedStages ms{};
     ms.n = (int)rad.size();
     ms.L = L;
+    ms.tw_o2 = tw_o2 ? 1 : 0;
     const long long lines0 = lv.empty() ? 1 : std::max<long long>(1, lv[0].n);
     const size_t budget = (size_t)env_int_or("FFTB200_MIXED_TILE_KB", 16) << 10;  // one shared-memory buffer
     const bool half = io == MIXED_R2C_HALF || io == MIXED_C2R_HALF;  // (L is half the real length; one more shared-memory pass)
@@ -727,32 +734,8 @@ static bool build_mixed(Builder &B) {
         if ((is_pow2(n[d]) && n[d] <= maxL) || mixed_axis_ok(n[d], P->prec)) ++short_axes; else ++long_axes;
     }
     if (total == 1) return false;
-    if (long_axes == 1 && short_axes == 0 && n[last] > 1 && !real && !c2r) {
-        // a single line too long for one tile: L = N1 N2, a strided pass over n1 with the w_L^(k1 n2) twiddle into a work
-        // buffer, then a contiguous pass over n2 with a transposing store (both factors as balanced as the radices allow)
-        const long long Lw = n[last];
-        if (Lw > (1ll << 31) - 1) return false;
-        long long N1 = 0;
-        for (long long a = (long long)std::sqrt((double)Lw) + 1; a >= 2; --a) {
-            if (Lw % a) continue;
-            if (mixed_axis_ok(a, P->prec) && mixed_axis_ok(Lw / a, P->prec)) { N1 = a; break; }
-        }
-        if (!N1) return false;
-        const long long N2 = Lw / N1;  // N1 <= N2: the strided pass (whole 128-byte columns in shared memory) gets the shorter factor
-        const size_t ce = P->prec ? 16 : 8;
-        P->work_bytes = (size_t)Lw * P->batch * ce;
-        P->work[0] = B.alloc(P->work_bytes);
-        if (!P->work[0]) return false;
-        if (!add_mixed_pass(B, false, (int)N1, N2, N2, {{N2, 1, 1}, {(long long)P->batch, P->in_stride[0], Lw}}, BUF_IN, BUF_WORK0,
-                            "two-pass line 1/2", MIXED_TW, Lw))
-            return false;
-        if (!add_mixed_pass(B, true, (int)N2, 1, N1, {{N1, N2, 1}, {(long long)P->batch, Lw, P->out_stride[0]}}, BUF_WORK0, BUF_OUT,
-                            "two-pass line 2/2", MIXED_RC))
-            return false;
-        P->inplace_ok = true;  // every pass goes through the work buffer
-        return true;
-    }
-    if (long_axes) return false;
+    if (long_axes && c2r) return false;
+    if (long_axes && real && !((is_pow2(n[last]) && n[last] <= maxL) || mixed_axis_ok(n[last], P->prec))) return false;
     if ((real || c2r) && n[last] < 2) return false;
     const long long nc = n[last] / 2 + 1;
     // one pass along `axis`: the tuned power-of-two tile kernel when there is one, else the mixed-radix kernel
@@ -850,17 +833,62 @@ static bool build_mixed(Builder &B) {
         }
         first = false;
     }
+    if (long_axes) {
+        // two-pass axes go through a work buffer laid out like the output array
+        P->work_bytes = P->span_out;
+        P->work[0] = B.alloc(P->work_bytes);
+        if (!P->work[0]) return false;
+    }
+    bool all_long = true;
     for (int axis = real ? last - 1 : last; axis >= 0; --axis) {
         if (n[axis] == 1) continue;
         const bool row = axis == last;
         const long long in_ls = first ? P->in_stride[axis + 1] : P->out_stride[axis + 1];
         const long long out_ls = P->out_stride[axis + 1];
-        if (!axis_pass(row, (int)n[axis], in_ls, out_ls, levels_for(axis, first), first ? BUF_IN : BUF_OUT, BUF_OUT,
-                       row ? "last axis" : "strided axis"))
+        const int src = first ? BUF_IN : BUF_OUT;
+        const bool is_short = (is_pow2(n[axis]) && n[axis] <= maxL) || mixed_axis_ok(n[axis], P->prec);
+        if (is_short) {
+            all_long = false;
+            if (!axis_pass(row, (int)n[axis], in_ls, out_ls, levels_for(axis, first), src, BUF_OUT, row ? "last axis" : "strided axis"))
+                return false;
+            first = false;
+            continue;
+        }
+        // A line too long for one tile: L = N1 N2 (n = n1 N2 + n2, k = k1 + N1 k2), both factors as balanced as the radices
+        // allow.  Pass 1: strided transform over n1, store times w_L^(k1 n2), into the work buffer (output layout).
+        // Pass 2: transform over n2, stored at k2 N1 + k1 of the output.
+        const long long Lw = n[axis];
+        if (Lw > (1ll << 31) - 1) return false;
+        long long N1 = 0;
+        for (long long a = (long long)std::sqrt((double)Lw) + 1; a >= 2; --a) {
+            if (Lw % a) continue;
+            if (mixed_axis_ok(a, P->prec) && mixed_axis_ok(Lw / a, P->prec)) { N1 = a; break; }
+        }
+        if (!N1) return false;
+        const long long N2 = Lw / N1;  // N1 <= N2: the strided pass (whole 128-byte columns in shared memory) gets the shorter one
+        std::vector<Level> other = levels_for(axis, first);  // dims after the axis (fastest first), dims before it, batch
+        std::vector<Level> other_w = other;                   // the same indices inside the work buffer / output
+        for (Level &l : other_w) l.is = l.os;
+        const size_t n_inner_levels = (size_t)(last - axis);  // levels of `other` that are faster than the axis
+        Level l_n2{N2, in_ls, out_ls};
+        l_n2.keep = true;
+        std::vector<Level> lv1(other.begin(), other.begin() + n_inner_levels);
+        lv1.push_back(l_n2);
+        lv1.insert(lv1.end(), other.begin() + n_inner_levels, other.end());
+        if (!add_mixed_pass(B, false, (int)N1, N2 * in_ls, N2 * out_ls, lv1, src, BUF_WORK0, "two-pass axis 1/2", MIXED_TW, Lw, !row))
             return false;
+        std::vector<Level> lv2(other_w.begin(), other_w.begin() + n_inner_levels);
+        lv2.push_back({N1, N2 * out_ls, out_ls});
+        lv2.insert(lv2.end(), other_w.begin() + n_inner_levels, other_w.end());
+        if (row) {
+            if (!add_mixed_pass(B, true, (int)N2, 1, N1, lv2, BUF_WORK0, BUF_OUT, "two-pass axis 2/2", MIXED_RC)) return false;
+        } else {
+            if (!add_mixed_pass(B, false, (int)N2, out_ls, N1 * out_ls, lv2, BUF_WORK0, BUF_OUT, "two-pass axis 2/2")) return false;
+        }
         first = false;
     }
-    P->inplace_ok = layouts_coincide(P);
+    // in place: tile-wise in-place passes need coinciding layouts; two-pass axes read everything before they write the output
+    P->inplace_ok = layouts_coincide(P) || (all_long && !real);
     return true;
 }
 

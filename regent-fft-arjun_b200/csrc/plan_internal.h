@@ -119,7 +119,10 @@ int env_int_or(const char *name, int dflt);  // tuning knobs, re
 bool is_pow2(long long v);
 int ilog2ll(long long v);
 
-struct Level { long long n, is, os; };
+struct Level {
+    long long n, is, os;
+    bool keep = false;  // never merged with its neighbours (its index has a meaning of its own: the n2 of a two-pass line)
+};
 
 // device tables of one plan under construction
 struct Builder {

@@ -848,6 +848,19 @@ def test_long_mixed_radix_lines_run_two_passes(L, oracle):
         assert err <= tol, (kind, shape, batch, err)
         back, _ = gpu_fft(L, kind, got, shape, batch=batch, direction=+1)
         assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * tol, (kind, shape, "round trip")
+    # long axes inside 2-D / 3-D shapes, in any position, power-of-two ones included (no tile kernel reaches 2^15 fp64)
+    for kind, shape in [("z2z", (20000, 6)), ("z2z", (6, 20000)), ("z2z", (32768, 8)), ("c2c", (8, 65536)), ("z2z", (4, 10000, 6)),
+                        ("z2z", (10000, 3, 4)), ("z2z", (12000, 14000 // 1000)), ("d2z", (20000, 12)), ("z2z", (7000, 9000 // 1000))]:
+        _, dt_in, _ = _kinds(L)[kind]
+        x = oracle.synth(shape, dt_in, 1720)
+        got, desc = gpu_fft(L, kind, x, shape)
+        assert "two-pass axis" in desc and "generic" not in desc, (shape, desc)
+        tol = oracle.tolerance(int(np.prod(shape)), kind == "c2c")
+        err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape))
+        assert err <= tol, (kind, shape, err, desc)
+        if kind != "d2z":
+            back, _ = gpu_fft(L, kind, got, shape, direction=+1)
+            assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * tol, (kind, shape, "round trip")
     # in place
     ftype, dt_in, _ = _kinds(L)["z2z"]
     x = oracle.synth((30000,), dt_in, 1710)
@@ -1040,8 +1053,8 @@ def test_mixed_radix_lengths_run_one_kernel_per_axis(L, oracle):
         torch.cuda.synchronize()
         L.destroy(h)
         assert oracle.rel_l2(buf.cpu().numpy(), cpu_fft(oracle, "z2z", x, shape)) <= oracle.tolerance(int(np.prod(shape)), False)
-    # long axes of multi-dimensional shapes, and other primes, stay on the generic path
-    for shape in [(4 * 5 ** 5, 2), (17 * 8,)]:
+    # other primes stay on the generic path
+    for shape in [(2, 6, 4 * 5 ** 5 * 17), (17 * 8,)]:
         _, dt_in, _ = _kinds(L)["z2z"]
         x = oracle.synth(shape, dt_in, 955)
         got, desc = gpu_fft(L, "z2z", x, shape)
