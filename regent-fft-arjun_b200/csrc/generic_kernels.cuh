@@ -131,6 +131,65 @@ __global__ void gen_scatter_real_kernel(const cplx<T> *__restrict__ packed, T *_
     }
 }
 
+// ---- long real lines (2 Lh reals, Lh too long for one shared-memory tile): the even/odd passes of the half-length
+// scheme as global-memory kernels around the two-pass complex transform of z[m] = x[2m] + i x[2m+1]
+// (mixed_kernel.cuh has the shared-memory form and the formulas; fftw-3.3.8/rdft/ct-hc2c.c:59-70 on the CPU path).
+// `lay` enumerates the LINES (all indices but the last axis): offset of a line's first complex element.
+__device__ __forceinline__ long long gen_line_offset(const GenLayout &lay, long long line) {
+    long long rem = line, off = 0;
+#pragma unroll
+    for (int d = 3; d >= 0; --d) {
+        if (d < lay.nd) {
+            const long long q = rem / lay.n[d];
+            off += (rem - q * lay.n[d]) * lay.stride[d];
+            rem = q;
+        }
+    }
+    return off;
+}
+
+// in place on the half-spectrum lines: Z[0 .. Lh) -> X[0 .. Lh];  tw[k] = w_{2 Lh}^k, k in [0, Lh/2]
+template <typename T>
+__global__ void gen_r2c_post_kernel(cplx<T> *__restrict__ data, GenLayout lay, long long total, int Lh,
+                                    const cplx<T> *__restrict__ tw) {
+    using C = cplx<T>;
+    const int pairs = Lh / 2 + 1;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long line = e / pairs;
+        const int k = (int)(e - line * pairs);
+        C *z = data + gen_line_offset(lay, line);
+        const C za = z[k], zb = z[k == 0 ? 0 : Lh - k];
+        const C wk = __ldg(tw + k);
+        const C ev = mk<T>((T)0.5 * (za.x + zb.x), (T)0.5 * (za.y - zb.y));
+        const C b = mk<T>((T)0.5 * (za.y + zb.y), (T)-0.5 * (za.x - zb.x));
+        const C wb = cmul(wk, b);
+        z[k] = mk<T>(ev.x + wb.x, ev.y + wb.y);
+        z[Lh - k] = mk<T>(ev.x - wb.x, -(ev.y - wb.y));
+    }
+}
+
+// half spectrum X[0 .. Lh] (lines of lay_in) -> Z'[0 .. Lh) (lines of lay_out), the spectrum whose backward complex
+// transform is x[2m] + i x[2m+1]
+template <typename T>
+__global__ void gen_c2r_pre_kernel(const cplx<T> *__restrict__ in, cplx<T> *__restrict__ out, GenLayout lay_in,
+                                   GenLayout lay_out, long long total, int Lh, const cplx<T> *__restrict__ tw) {
+    using C = cplx<T>;
+    const int pairs = Lh / 2 + 1;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long line = e / pairs;
+        const int k = (int)(e - line * pairs);
+        const C *x = in + gen_line_offset(lay_in, line);
+        C *z = out + gen_line_offset(lay_out, line);
+        const C xa = x[k], xb = x[Lh - k];
+        const C wk = __ldg(tw + k);
+        const C ee = mk<T>(xa.x + xb.x, xa.y - xb.y);
+        const C dd = mk<T>(xa.x - xb.x, xa.y + xb.y);
+        const C oo = mk<T>(dd.x * wk.x + dd.y * wk.y, dd.y * wk.x - dd.x * wk.y);
+        z[k] = mk<T>(ee.x - oo.y, ee.y + oo.x);
+        if (k > 0) z[Lh - k] = mk<T>(ee.x + oo.y, oo.x - ee.y);
+    }
+}
+
 // in-place scaling of the elements of a layout (normalisation helper); COMPONENTS = 2 for complex, 1 for real elements
 template <typename T, int COMPONENTS>
 __global__ void gen_scale_kernel(T *__restrict__ data, GenLayout lay, long long total, T factor) {

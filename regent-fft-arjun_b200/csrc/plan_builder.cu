@@ -718,6 +718,8 @@ static bool add_mixed_pass(Builder &B, bool row, int L, long long in_ls, long lo
     return B.err == FFTB200_SUCCESS;
 }
 
+static unsigned grid_for(long long total);
+
 static bool build_mixed(Builder &B) {
     Plan *P = B.P;
     const int rank = P->rank, last = rank - 1;
@@ -726,16 +728,64 @@ static bool build_mixed(Builder &B) {
     if (P->in_stride[rank] != 1 || P->out_stride[rank] != 1) return false;
     const bool real = P->real, c2r = P->c2r;
     const int maxL = max_tile_length(P->prec);
+    auto short_axis = [&](long long v) { return (is_pow2(v) && v <= maxL) || mixed_axis_ok(v, P->prec); };
+    // (a real last axis of even length only needs its half to fit one tile)
+    const bool last_long = n[last] > 1 && !short_axis(n[last]) &&
+                           !((real || c2r) && !(n[last] & 1) && mixed_axis_ok(n[last] / 2, P->prec));
     long long total = 1;
-    int long_axes = 0, short_axes = 0;
+    int long_axes = 0;
     for (int d = 0; d < rank; ++d) {
         total *= n[d];
         if (n[d] == 1) continue;
-        if ((is_pow2(n[d]) && n[d] <= maxL) || mixed_axis_ok(n[d], P->prec)) ++short_axes; else ++long_axes;
+        if (d == last ? last_long : !short_axis(n[d])) ++long_axes;
     }
     if (total == 1) return false;
-    if (long_axes && c2r) return false;
-    if (long_axes && real && !((is_pow2(n[last]) && n[last] <= maxL) || mixed_axis_ok(n[last], P->prec))) return false;
+    if (c2r && long_axes > (last_long ? 1 : 0)) return false;  // (C2R: only the last axis may be a two-pass line)
+    if ((real || c2r) && last_long && (n[last] & 1)) return false;  // long real lines: even lengths (half-length scheme)
+    // L = N1 N2 with both factors on the one-tile path, as balanced as the radices allow (N1 <= N2); 0 if there is none
+    auto split_long = [&](long long Lw) -> long long {
+        if (Lw > (1ll << 31) - 1) return 0;
+        for (long long a = (long long)std::sqrt((double)Lw) + 1; a >= 2; --a) {
+            if (Lw % a) continue;
+            if (mixed_axis_ok(a, P->prec) && mixed_axis_ok(Lw / a, P->prec)) return a;
+        }
+        return 0;
+    };
+    // A line too long for one tile: L = N1 N2 (n = n1 N2 + n2, k = k1 + N1 k2).  Pass 1: strided transform over n1, store
+    // times w_L^(k1 n2), into work buffer `wbuf` (laid out like the destination).  Pass 2: transform over n2, stored at
+    // k2 N1 + k1 of BUF_OUT.  `other`: the remaining index levels, fastest first, the first n_inner_levels of them faster
+    // than the axis; is = source strides, os = destination strides.
+    auto two_pass = [&](bool row, long long Lw, long long in_ls, long long out_ls, const std::vector<Level> &other,
+                        size_t n_inner_levels, int src, int wbuf) -> bool {
+        const long long N1 = split_long(Lw);
+        if (!N1) return false;
+        const long long N2 = Lw / N1;  // the strided pass (whole 128-byte columns in shared memory) gets the shorter factor
+        std::vector<Level> other_w = other;
+        for (Level &l : other_w) l.is = l.os;
+        Level l_n2{N2, in_ls, out_ls};
+        l_n2.keep = true;
+        std::vector<Level> lv1(other.begin(), other.begin() + n_inner_levels);
+        lv1.push_back(l_n2);
+        lv1.insert(lv1.end(), other.begin() + n_inner_levels, other.end());
+        if (!add_mixed_pass(B, false, (int)N1, N2 * in_ls, N2 * out_ls, lv1, src, wbuf, "two-pass axis 1/2", MIXED_TW, Lw, !row))
+            return false;
+        std::vector<Level> lv2(other_w.begin(), other_w.begin() + n_inner_levels);
+        lv2.push_back({N1, N2 * out_ls, out_ls});
+        lv2.insert(lv2.end(), other_w.begin() + n_inner_levels, other_w.end());
+        if (row) return add_mixed_pass(B, true, (int)N2, 1, N1, lv2, wbuf, BUF_OUT, "two-pass axis 2/2", MIXED_RC);
+        return add_mixed_pass(B, false, (int)N2, out_ls, N1 * out_ls, lv2, wbuf, BUF_OUT, "two-pass axis 2/2");
+    };
+    // line layouts (every index but the last axis) for the even/odd kernels of long real lines, strides in complex elements
+    auto line_layout = [&](const long long *strides /* [batch, d0 ..] */, long long div) {
+        GenLayout g{};
+        g.nd = rank;  // batch + (rank - 1) leading dims
+        g.n[0] = P->batch;
+        g.stride[0] = strides[0] / div;
+        for (int d = 0; d < last; ++d) { g.n[d + 1] = n[d]; g.stride[d + 1] = strides[d + 1] / div; }
+        return g;
+    };
+    long long n_lines = P->batch;
+    for (int d = 0; d < last; ++d) n_lines *= n[d];
     if ((real || c2r) && n[last] < 2) return false;
     const long long nc = n[last] / 2 + 1;
     // one pass along `axis`: the tuned power-of-two tile kernel when there is one, else the mixed-radix kernel
@@ -778,6 +828,35 @@ static bool build_mixed(Builder &B) {
         }
         bool even_out = true;
         for (int d = 0; d < rank; ++d) even_out = even_out && !(P->out_stride[d] & 1);
+        if (last_long) {
+            // long real line: even/odd pre-pass (half spectrum -> Z' in the output lines), then the two-pass backward
+            // complex transform of Z' through a second work buffer, stored as pairs of reals
+            if (!even_out) return false;
+            const long long Lh = n[last] / 2;
+            if (!split_long(Lh)) return false;
+            P->work[1] = B.alloc(P->span_out);
+            if (!P->work[1]) return false;
+            Launch pre;
+            pre.kind = Launch::C2R_PRE;
+            pre.lay2 = line_layout(cs, 1);
+            pre.lay = line_layout(P->out_stride, 2);
+            pre.L = (int)Lh;
+            pre.total = n_lines * (Lh / 2 + 1);
+            pre.bhat = B.table(2 * Lh, Lh / 2 + 1, false);
+            if (!pre.bhat) return false;
+            pre.src = cur;
+            pre.dst = BUF_OUT;
+            pre.grid = grid_for(pre.total);
+            pre.algo_bytes = (unsigned long long)n_lines * (unsigned long long)(2 * Lh + 1) * ce;
+            pre.desc = "c2r even/odd pre-pass (half spectrum -> spectrum of the packed pairs)";
+            P->launches.push_back(pre);
+            std::vector<Level> other;
+            for (int d = last - 1; d >= 0; --d) other.push_back({n[d], P->out_stride[d + 1] / 2, P->out_stride[d + 1] / 2});
+            other.push_back({(long long)P->batch, P->out_stride[0] / 2, P->out_stride[0] / 2});
+            if (!two_pass(true, Lh, 1, 1, other, 0, BUF_OUT, BUF_WORK1)) return false;
+            P->inplace_ok = outer_axes > 1 || P->batch == 1 || P->out_stride[0] == 2 * P->in_stride[0];
+            return true;
+        }
         const bool tile_last = is_pow2(n[last]) && n[last] >= 4 && even_out && find_tile_kernel(P->prec, V_RR_C2R, (int)(n[last] / 2));
         std::vector<Level> lv;
         const long long div = tile_last ? 2 : 1;  // (the tile kernel addresses the reals as complex pairs)
@@ -819,7 +898,31 @@ static bool build_mixed(Builder &B) {
         bool even_in = true;
         for (int d = 0; d < rank; ++d) even_in = even_in && !(P->in_stride[d] & 1);
         std::vector<Level> lv = levels_for(last, true);
-        if (is_pow2(n[last]) && n[last] >= 4 && even_in && find_tile_kernel(P->prec, V_RR_R2C, (int)(n[last] / 2))) {
+        if (last_long) {
+            // long real line: two-pass complex transform of the packed pairs into the output lines, then the even/odd
+            // pass in place on them
+            if (!even_in) return false;
+            const long long Lh = n[last] / 2;
+            P->work_bytes = P->span_out;
+            P->work[0] = B.alloc(P->work_bytes);
+            if (!P->work[0]) return false;
+            std::vector<Level> other = lv;
+            for (Level &l : other) l.is /= 2;
+            if (!two_pass(true, Lh, 1, 1, other, 0, BUF_IN, BUF_WORK0)) return false;
+            Launch post;
+            post.kind = Launch::R2C_POST;
+            post.lay = line_layout(P->out_stride, 1);
+            post.L = (int)Lh;
+            post.total = n_lines * (Lh / 2 + 1);
+            post.bhat = B.table(2 * Lh, Lh / 2 + 1, false);
+            if (!post.bhat) return false;
+            post.src = BUF_OUT;
+            post.dst = BUF_OUT;
+            post.grid = grid_for(post.total);
+            post.algo_bytes = (unsigned long long)n_lines * (unsigned long long)(2 * Lh + 1) * (P->prec ? 16 : 8);
+            post.desc = "r2c even/odd post-pass (in place on the half-spectrum lines)";
+            P->launches.push_back(post);
+        } else if (is_pow2(n[last]) && n[last] >= 4 && even_in && find_tile_kernel(P->prec, V_RR_R2C, (int)(n[last] / 2))) {
             for (Level &l : lv) l.is /= 2;  // input addressed as packed complex pairs
             if (!add_tile_pass(B, V_RR_R2C, (int)(n[last] / 2), 1, 1, lv, BUF_IN, BUF_OUT, 0, "axis r2c")) return false;
         } else {
@@ -833,62 +936,31 @@ static bool build_mixed(Builder &B) {
         }
         first = false;
     }
-    if (long_axes) {
+    if (long_axes && !P->work[0]) {
         // two-pass axes go through a work buffer laid out like the output array
         P->work_bytes = P->span_out;
         P->work[0] = B.alloc(P->work_bytes);
         if (!P->work[0]) return false;
     }
-    bool all_long = true;
+    bool first_two_pass = real && last_long;  // the first pass reads all of the input before anything is written to the output
     for (int axis = real ? last - 1 : last; axis >= 0; --axis) {
         if (n[axis] == 1) continue;
         const bool row = axis == last;
         const long long in_ls = first ? P->in_stride[axis + 1] : P->out_stride[axis + 1];
         const long long out_ls = P->out_stride[axis + 1];
         const int src = first ? BUF_IN : BUF_OUT;
-        const bool is_short = (is_pow2(n[axis]) && n[axis] <= maxL) || mixed_axis_ok(n[axis], P->prec);
-        if (is_short) {
-            all_long = false;
+        if (short_axis(n[axis])) {
             if (!axis_pass(row, (int)n[axis], in_ls, out_ls, levels_for(axis, first), src, BUF_OUT, row ? "last axis" : "strided axis"))
                 return false;
             first = false;
             continue;
         }
-        // A line too long for one tile: L = N1 N2 (n = n1 N2 + n2, k = k1 + N1 k2), both factors as balanced as the radices
-        // allow.  Pass 1: strided transform over n1, store times w_L^(k1 n2), into the work buffer (output layout).
-        // Pass 2: transform over n2, stored at k2 N1 + k1 of the output.
-        const long long Lw = n[axis];
-        if (Lw > (1ll << 31) - 1) return false;
-        long long N1 = 0;
-        for (long long a = (long long)std::sqrt((double)Lw) + 1; a >= 2; --a) {
-            if (Lw % a) continue;
-            if (mixed_axis_ok(a, P->prec) && mixed_axis_ok(Lw / a, P->prec)) { N1 = a; break; }
-        }
-        if (!N1) return false;
-        const long long N2 = Lw / N1;  // N1 <= N2: the strided pass (whole 128-byte columns in shared memory) gets the shorter one
-        std::vector<Level> other = levels_for(axis, first);  // dims after the axis (fastest first), dims before it, batch
-        std::vector<Level> other_w = other;                   // the same indices inside the work buffer / output
-        for (Level &l : other_w) l.is = l.os;
-        const size_t n_inner_levels = (size_t)(last - axis);  // levels of `other` that are faster than the axis
-        Level l_n2{N2, in_ls, out_ls};
-        l_n2.keep = true;
-        std::vector<Level> lv1(other.begin(), other.begin() + n_inner_levels);
-        lv1.push_back(l_n2);
-        lv1.insert(lv1.end(), other.begin() + n_inner_levels, other.end());
-        if (!add_mixed_pass(B, false, (int)N1, N2 * in_ls, N2 * out_ls, lv1, src, BUF_WORK0, "two-pass axis 1/2", MIXED_TW, Lw, !row))
-            return false;
-        std::vector<Level> lv2(other_w.begin(), other_w.begin() + n_inner_levels);
-        lv2.push_back({N1, N2 * out_ls, out_ls});
-        lv2.insert(lv2.end(), other_w.begin() + n_inner_levels, other_w.end());
-        if (row) {
-            if (!add_mixed_pass(B, true, (int)N2, 1, N1, lv2, BUF_WORK0, BUF_OUT, "two-pass axis 2/2", MIXED_RC)) return false;
-        } else {
-            if (!add_mixed_pass(B, false, (int)N2, out_ls, N1 * out_ls, lv2, BUF_WORK0, BUF_OUT, "two-pass axis 2/2")) return false;
-        }
+        if (first) first_two_pass = true;
+        if (!two_pass(row, n[axis], in_ls, out_ls, levels_for(axis, first), (size_t)(last - axis), src, BUF_WORK0)) return false;
         first = false;
     }
-    // in place: tile-wise in-place passes need coinciding layouts; two-pass axes read everything before they write the output
-    P->inplace_ok = layouts_coincide(P) || (all_long && !real);
+    // in place: tile-wise in-place passes need coinciding layouts; a two-pass axis reads everything before it writes the output
+    P->inplace_ok = layouts_coincide(P) || first_two_pass;
     return true;
 }
 

@@ -127,6 +127,12 @@ template <typename T> static cudaError_t launch_generic(const Launch &ln, const 
         case Launch::GEN_SCATTER_REAL:
             gen_scatter_real_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (T *)dst, ln.lay, ln.total);
             break;
+        case Launch::R2C_POST:
+            gen_r2c_post_kernel<T><<<ln.grid, 256, 0, st>>>((C *)dst, ln.lay, ln.total, ln.L, (const C *)ln.bhat);
+            break;
+        case Launch::C2R_PRE:
+            gen_c2r_pre_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.lay2, ln.lay, ln.total, ln.L, (const C *)ln.bhat);
+            break;
         case Launch::BLU_PRE:
             gen_blu_pre_kernel<T><<<ln.grid, 256, 0, st>>>((const C *)src, (C *)dst, ln.chirp, ln.outer, ln.L, ln.M, ln.inner);
             break;

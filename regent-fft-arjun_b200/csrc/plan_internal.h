@@ -20,7 +20,7 @@ namespace fftb200 {
 enum BufSel { BUF_IN = 0, BUF_OUT = 1, BUF_WORK0 = 2, BUF_WORK1 = 3, BUF_BLU = 4 };
 
 struct Launch {
-    enum Kind { TILE, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER, BLU_PRE, BLU_MUL, BLU_POST, GEN_GATHER_HERM, GEN_SCATTER_REAL, MIXED } kind = TILE;
+    enum Kind { TILE, GEN_GATHER, GEN_STAGE, GEN_TRUNC, GEN_SCATTER, BLU_PRE, BLU_MUL, BLU_POST, GEN_GATHER_HERM, GEN_SCATTER_REAL, MIXED, R2C_POST, C2R_PRE } kind = TILE;
     // TILE
     const TileKernelInfo *ki = nullptr;
     TileParams tp{};
@@ -30,6 +30,7 @@ struct Launch {
     bool mixed_row = false;
     // generic
     GenLayout lay{};
+    GenLayout lay2{};  // C2R_PRE: the input lines (lay: the output lines)
     long long total = 0, outer = 0, inner = 0;
     int L = 0, p = 0, Ns = 0, Lc = 0;
     const double2 *gtw = nullptr;

@@ -811,7 +811,9 @@ def test_inverse_real_transforms(L, oracle):
                                             ("z2d", (1021,), "Hermitian"), ("c2r", (6, 127), "Hermitian"),
                                             ("z2d", (9, 7), "mixed-radix c2r-row"), ("z2d", (96, 100, 90), "mixed-radix c2r-row"),
                                             ("c2r", (15, 1001), "mixed-radix c2r-row"), ("z2d", (6, 1024), "c2r-row"),
-                                            ("z2d", (128, 6), "mixed-radix c2r-row")]):
+                                            ("z2d", (128, 6), "mixed-radix c2r-row"), ("z2d", (1000000,), "c2r even/odd pre-pass"),
+                                            ("z2d", (4, 100000), "c2r even/odd pre-pass"), ("c2r", (6, 10, 60000), "c2r even/odd pre-pass"),
+                                            ("z2d", (10000,), "half-length")]):
         single = kind == "c2r"
         rdt, cdt = (np.float32, np.complex64) if single else (np.float64, np.complex128)
         ftype = L.C2R if single else L.Z2D
@@ -850,15 +852,18 @@ def test_long_mixed_radix_lines_run_two_passes(L, oracle):
         assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * tol, (kind, shape, "round trip")
     # long axes inside 2-D / 3-D shapes, in any position, power-of-two ones included (no tile kernel reaches 2^15 fp64)
     for kind, shape in [("z2z", (20000, 6)), ("z2z", (6, 20000)), ("z2z", (32768, 8)), ("c2c", (8, 65536)), ("z2z", (4, 10000, 6)),
-                        ("z2z", (10000, 3, 4)), ("z2z", (12000, 14000 // 1000)), ("d2z", (20000, 12)), ("z2z", (7000, 9000 // 1000))]:
+                        ("z2z", (10000, 3, 4)), ("z2z", (12000, 14)), ("d2z", (20000, 12)), ("z2z", (7000, 9)),
+                        ("d2z", (1000000,)), ("r2c", (2000000,)), ("d2z", (3, 200000)), ("d2z", (7000, 14000)), ("d2z", (10000,))]:
         _, dt_in, _ = _kinds(L)[kind]
         x = oracle.synth(shape, dt_in, 1720)
         got, desc = gpu_fft(L, kind, x, shape)
-        assert "two-pass axis" in desc and "generic" not in desc, (shape, desc)
-        tol = oracle.tolerance(int(np.prod(shape)), kind == "c2c")
+        assert ("two-pass axis" in desc or shape == (10000,)) and "generic" not in desc, (shape, desc)
+        if kind in ("d2z", "r2c") and shape[-1] >= 100000:
+            assert "even/odd post-pass" in desc, desc
+        tol = oracle.tolerance(int(np.prod(shape)), kind in ("c2c", "r2c"))
         err = oracle.rel_l2(got, cpu_fft(oracle, kind, x, shape))
         assert err <= tol, (kind, shape, err, desc)
-        if kind != "d2z":
+        if kind in ("z2z", "c2c"):
             back, _ = gpu_fft(L, kind, got, shape, direction=+1)
             assert oracle.rel_l2(back / np.prod(shape), x) <= 2 * tol, (kind, shape, "round trip")
     # in place
