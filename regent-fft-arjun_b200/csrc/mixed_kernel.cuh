@@ -1,16 +1,17 @@
-// mixed_kernel.cuh — one-pass-per-axis shared-memory FFT for lengths that are NOT powers of two:
-// L = 2^a 3^b 5^c 7^d 11^e 13^f (96, 100, 120, 360, 384, 480, 1000, 1001, 1536, 6000, ...).
+// mixed_kernel.cuh — shared-memory FFT passes for the lengths the power-of-two tile kernels do not cover:
+// L = 2^a 3^b 5^c 7^d 11^e 13^f (96, 100, 120, 360, 384, 480, 1000, 1001, 1536, 6000, ...) in ONE pass per axis, and axes
+// too long for one tile (10^4 ... 4 * 10^7 points, powers of two included) in two.
 //
 // The power-of-two tile kernels (tile_kernel.cuh) keep R points per thread in registers across all stages and are tuned to
-// the HBM roofline; this kernel is the general form of the same idea for the sizes they do not cover.  A CTA loads a tile
-// of W lines of length L, runs one Stockham autosort stage per radix - the first reading global memory, the last writing
-// it, the exchanges in between through shared memory - and so makes one HBM round trip per axis instead of the generic
-// path's gather + one global-memory pass per prime factor + scatter.  The radices are the in-register DFTs of radix_dft.cuh (2 ... 16,
-// products of 2, 3, 5, 7, 11, 13), chosen at plan time so that a line needs as few stages as possible (1000 = 10 x 10 x 10,
-// 384 = 6 x 8 x 8, 96 = 12 x 8); every stage has its own twiddle table, laid out so that a warp reads it as contiguous
-// runs.  The reference's CPU path covers these sizes with FFTW's n1_3 / n1_5 / n1_7 / ... codelets and its generic
-// Cooley-Tukey solver (fftw-3.3.8/dft/ct.c, dft/scalar/codelets/); its own test shapes 3, 5, {3,2,2}, {3,3,2}
-// (test/fft_test.rg:143,247,328,349) are of this kind.
+// the HBM roofline; this kernel is the general form of the same idea.  A CTA owns a tile of W lines of length L and runs
+// one Stockham autosort stage per radix - the first reading global memory, the last writing it, the exchanges in between
+// through shared memory - so an axis costs one HBM round trip instead of the generic path's gather + one global-memory
+// pass per prime factor + scatter.  The radices are the in-register DFTs of radix_dft.cuh (2 ... 16, products of 2, 3, 5,
+// 7, 11, 13), chosen at plan time so that a line needs as few stages as possible (1000 = 10 x 10 x 10, 384 = 6 x 8 x 8,
+// 96 = 12 x 8); every stage has its own twiddle table, laid out so that a warp reads it as contiguous runs.  L, W and the
+// radices are run-time values (no per-length instantiation).  The reference's CPU path covers these sizes with FFTW's
+// n1_3 / n1_5 / n1_7 / ... codelets and its Cooley-Tukey solver (fftw-3.3.8/dft/ct.c, dft/scalar/codelets/); its own test
+// shapes 3, 5, {3,2,2}, {3,3,2} (test/fft_test.rg:143,247,328,349) are of this kind.
 //
 // Stage s (radix P, Ns = product of the earlier radices, Lp = L / P), butterfly j in [0, Lp):
 //     k = j mod Ns;   a_t = x[j + t Lp] * w_L^(t k L / (Ns P)),  t in [0, P);   y[(j - k) P + k + q Ns] = DFT_P(a)[q]
