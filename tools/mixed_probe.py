@@ -39,7 +39,8 @@ def ours(x, y, shape, batch, ftype, mixed, env=None):
 for prec, shape, batch in [("z2z", (96, 96, 96), 1), ("z2z", (192, 192, 192), 1), ("z2z", (384, 384, 384), 1), ("z2z", (100, 100, 100), 1),
                            ("z2z", (360, 360), 64), ("z2z", (1000,), 16384), ("z2z", (1536, 1536), 4), ("z2z", (6000,), 2048),
                            ("c2c", (384, 384, 384), 1), ("c2c", (1000,), 32768), ("z2z", (720, 1280), 8),
-                           ("z2z", (1000000,), 8), ("z2z", (100000,), 64), ("c2c", (3000000,), 4), ("d2z", (384, 384, 384), 1), ("d2z", (1000,), 32768), ("r2c", (360, 360), 128), ("d2z", (1080, 1920), 4)]:
+                           ("z2z", (1000000,), 8), ("z2z", (100000,), 64), ("c2c", (3000000,), 4), ("d2z", (1000000,), 16), ("z2z", (16384, 16384), 1), ("z2z", (10000, 10000), 1),
+                           ("d2z", (384, 384, 384), 1), ("d2z", (1000,), 32768), ("r2c", (360, 360), 128), ("d2z", (1080, 1920), 4)]:
     real = prec in ("d2z", "r2c")
     dt = {"z2z": torch.complex128, "c2c": torch.complex64, "d2z": torch.float64, "r2c": torch.float32}[prec]
     ftype = {"z2z": L.Z2Z, "c2c": L.C2C, "d2z": L.D2Z, "r2c": L.R2C}[prec]
